@@ -1,0 +1,107 @@
+"""Pins the NumPy oracle (oracle/ba_oracle.py) to outputs of the unmodified reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+import ba_oracle as o
+from conftest import load_golden, problem_from_golden
+
+BA_CASES = ["ba_T30", "ba_T24_ragged", "ba_T40_noisy"]
+DV = np.array([1, 1, 1, 100, 100, 100.0])
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name", BA_CASES)
+def test_landmark_project(name):
+    g = load_golden(name); pr = problem_from_golden(g)
+    uv, Jg = o.landmark_project(pr["states0"], pr["xyz"], pr["intr"], pr["ii"])
+    assert rel(uv, g["uv"]) < 1e-12
+    assert rel(Jg, g["Jg"]) < 1e-9           # north_star tolerance: 1e-9 relative
+    assert np.abs(Jg[:, :, 6:]).max() == 0
+
+
+@pytest.mark.parametrize("name", BA_CASES)
+def test_predict_blocks(name):
+    g = load_golden(name); pr = problem_from_golden(g)
+    d = o.predict(pr["states0"], pr["cum_rot"], pr["time_idx"])
+    assert rel(d["r_pred"], g["pred_r_pred"]) < 1e-9
+    assert rel(DV[None, :, None] * d["Phi"], g["pred_Jf_self"]) < 1e-9
+    assert np.abs(g["pred_Jf_next"] + np.diag(DV)).max() == 0
+    assert rel(d["qgrad"], g["pred_qgrad"]) < 1e-9
+    assert rel(d["Hq_diag"], g["pred_Hq_diag"]) < 1e-9
+    assert rel(d["Hq_off"], g["pred_Hq_off"]) < 1e-9
+    assert rel(np.swapaxes(d["Hq_off"], 1, 2), g["pred_Hq_low"]) < 1e-9
+
+
+@pytest.mark.parametrize("name", BA_CASES)
+def test_skip_mode_forward(name):
+    g = load_golden(name); pr = problem_from_golden(g)
+    x, _ = o.propagate_pairs(pr["states0"], pr["time_idx"], mode="skip100", stm=False)
+    assert rel(x[:, :3], g["skip_pos"]) < 1e-12 and rel(x[:, 3:], g["skip_vel"]) < 1e-12
+
+
+def test_long_gap_modes():
+    g = load_golden("long_gap")
+    for mode, kp, kv in (("skip100", "skip_pos", "skip_vel"), ("step1s", "step_pos", "step_vel")):
+        x, Phi = o.propagate_pairs(g["states"], g["time_idx"], mode=mode, stm=True)
+        assert rel(x[:, :3], g[kp]) < 1e-11 and rel(x[:, 3:], g[kv]) < 1e-11
+    # STM = exact derivative of the discrete map: central finite differences on one pair
+    st = g["states"]; i = 1
+    _, Phi = o.propagate_pairs(st, g["time_idx"], mode="skip100", stm=True)
+    num = np.zeros((6, 6)); cols = [0, 1, 2, 7, 8, 9]
+    for k, c in enumerate(cols):
+        h = 1e-4 if c < 3 else 1e-7
+        sp = st.copy(); sm = st.copy(); sp[i, c] += h; sm[i, c] -= h
+        xp, _ = o.propagate_pairs(sp, g["time_idx"], mode="skip100", stm=False)
+        xm, _ = o.propagate_pairs(sm, g["time_idx"], mode="skip100", stm=False)
+        num[:, k] = (xp[i] - xm[i]) / (2 * h)
+    assert rel(Phi[i], num) < 1e-6
+
+
+@pytest.mark.parametrize("name", BA_CASES)
+@pytest.mark.parametrize("dense", [True, False])
+def test_ba_iterates_track_reference(name, dense):
+    """20 iterations (10 initialize + 10 full): states within 1 m / 1 mm/s of the reference at EVERY
+    iteration (measured: < 1e-4 m), LM damping schedule identical."""
+    g = load_golden(name); pr = problem_from_golden(g)
+    st, lam = pr["states0"].copy(), 1e-4
+    for it in range(20):
+        st, lam, H, info = o.ba_iteration(it, st, pr["cum_rot"], pr["uv"], pr["xyz"], pr["ii"], pr["time_idx"],
+                                          pr["intr"], pr["conf"], lam, initialize=(it < 10), dense=dense)
+        ref = g["states_hist"][it]
+        assert np.abs(st[:, :3] - ref[:, :3]).max() < 1e-3, it          # km -> 1 m
+        assert np.abs(st[:, 7:] - ref[:, 7:]).max() < 1e-6, it          # km/s -> 1 mm/s
+        assert np.abs(st[:, 3:7] - ref[:, 3:7]).max() < 1e-7, it
+        assert lam == g["lamda_hist"][it], it
+        assert rel(H, g["hessian_hist"][it]) < 1e-6, it
+
+
+def test_helpers():
+    g = load_golden("helpers")
+    assert rel(o.quat_mul(g["q1"], g["q2"]), g["qmul"]) < 1e-15
+    assert rel(o.quat_exp(g["d"]), g["qexp"]) < 1e-15
+    assert rel(o.quat_log(g["q1"]), g["qlog"]) < 1e-14
+    assert rel(o.quat_conj(g["q1"]), g["qconj"]) == 0
+    assert rel(o.attitude_jacobian(g["q1"]), g["Gq"]) == 0
+    assert rel(o.precompute_cum_rotations(g["omegas"], 1.0), g["cum_rot"]) < 1e-15
+    assert rel(o.compute_omega_from_quat(g["qtrack"], 1.0), g["omega_from_quat"]) < 1e-12
+    f = np.concatenate([g["x"][:, 3:], o.orbit_accel(g["x"][:, :3])], -1)
+    assert rel(f, g["f_torch"]) < 1e-15 and rel(f, g["f_np"]) < 1e-14
+    assert rel(o.rk4_step(g["x"], 1.0), g["rk4_1s"]) < 1e-15
+    assert rel(o.rk4_step(g["x"], 100.0), g["rk4_100s"]) < 1e-15
+    assert rel(o.rk4_step(g["x"], 1.0), g["step_np"]) < 1e-14
+    s_t, v_t, s_full, v_full = o.propagate_dynamics_init(g["pdi_state"], g["pdi_vel"], g["pdi_omega"], 4, 5, 1.0)
+    assert rel(s_t, g["pdi_states_t"]) < 1e-14 and rel(v_t, g["pdi_vel_t"]) < 1e-14
+    assert rel(s_full, g["pdi_states_full"]) < 1e-14 and rel(v_full, g["pdi_vel_full"]) < 1e-14
+
+
+def test_lower_median_and_weights_corner():
+    assert o.lower_median([4.0, 1.0, 3.0, 2.0]) == 2.0
+    r = np.array([[0.0, 1.0], [2.0, -3.0]])
+    w, c = o.robust_weights(r, np.ones(2), 0)       # alpha == 2 -> pow(inf|nan, 0) == 1
+    assert c == 1.0 and np.all(w == 1.0)
+    w, c = o.robust_weights(r, np.ones(2), 3)
+    assert np.isfinite(w).all() and w.max() == 1.0
