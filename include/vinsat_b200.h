@@ -1,0 +1,173 @@
+/*
+ * vinsat_b200 -- C ABI of the B200-native VINSat estimation hot path.
+ *
+ * The reference (CMUAbstract/VINSat) is pure Python and has no FFI / plugin interface; its
+ * boundary for this path is the set of Python call signatures that estimation/od_pipe.py uses
+ * (SURVEY.md section 8(b)).  Every entry point below names the reference function(s) it replaces,
+ * as path:line under <reference>/estimation.  The Python mirror in vinsat_b200/ binds these with
+ * ctypes (see INTEGRATION.md for the stub a maintainer would add to the reference).
+ *
+ * Conventions
+ *   - fp64 everywhere; km, km/s, s, pixels; quaternions xyzw.
+ *   - state row   = [p(3) q(4) v(3)]              (reference `states`, (1,T,10))
+ *   - tangent row = [dp(3) dtheta(3) dv(3)]        (BA_filtering.py:56-60)
+ *   - all functions return 0 on success, a negative VINSAT_E* code on failure; the message is
+ *     available from vinsat_last_error().  No exceptions cross the boundary.
+ *   - `mem` says where the caller's buffers live: VINSAT_MEM_HOST (pageable or pinned host memory;
+ *     the library stages them through device memory) or VINSAT_MEM_DEVICE (CUDA device pointers on
+ *     the context's device; no copies).
+ *   - plain pointers and sizes only; no torch / numpy types.
+ */
+#ifndef VINSAT_B200_H
+#define VINSAT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VINSAT_ABI_VERSION 1
+
+enum {
+  VINSAT_OK = 0,
+  VINSAT_EINVAL = -1,  /* bad argument */
+  VINSAT_ECUDA = -2,   /* CUDA runtime error (message has the CUDA error string) */
+  VINSAT_ENOMEM = -3,
+  VINSAT_ENODEV = -4   /* no usable CUDA device */
+};
+
+enum { VINSAT_MEM_HOST = 0, VINSAT_MEM_DEVICE = 1 };
+
+/* Orbit propagator used inside the dynamics residual:
+ *   STEP1S  = BA_utils.py:73-87  `propagate_orbit_dynamics`       (CPU `predict`, the parity reference)
+ *   SKIP100 = BA_utils.py:52-71  `propagate_orbit_dynamics_skip`  (`predict_gpu`) */
+enum { VINSAT_MODE_STEP1S = 0, VINSAT_MODE_SKIP100 = 1 };
+
+typedef struct vinsat_ctx vinsat_ctx;
+typedef struct vinsat_batch vinsat_batch;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int vinsat_abi_version(void);
+int vinsat_device_count(void);
+int vinsat_ctx_create(int device, vinsat_ctx** out);
+int vinsat_ctx_destroy(vinsat_ctx* ctx);
+/* Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = library stream. */
+int vinsat_ctx_set_stream(vinsat_ctx* ctx, void* cuda_stream);
+int vinsat_ctx_synchronize(vinsat_ctx* ctx);
+const char* vinsat_last_error(const vinsat_ctx* ctx); /* ctx may be NULL: last global error */
+
+/* ---- a1: landmark_project  (BA/BA_utils.py:30-50, proj :7-17, apply_inverse_pose_transformation
+ *          :1052-1069, attitude_jacobian :19-28) -------------------------------------------------
+ * states [T,10], intrinsics [T,4] (fx fy cx cy), landmarks_xyz [M,3], ii [M] (frame of each obs,
+ * any order).  uv_out [M,2].  Jg_out [M,2,9] = [-Pi R^T | 2 Pi hat(p_c) | 0] or NULL (jacobian=False).
+ * uv_out is bit-identical to the reference (no FMA contraction in the forward projection). */
+int vinsat_landmark_project(vinsat_ctx* ctx, int mem, int64_t n_frames, int64_t n_obs,
+                            const double* states, const double* intrinsics, const double* landmarks_xyz,
+                            const int64_t* ii, double* uv_out, double* Jg_out);
+
+/* ---- a2-a4: predict / predict_gpu  (BA/BA_utils.py:457-527 / :529-602) -------------------------
+ * states [T,10]; cum_rot [T,4] = imu_meas[0,:,-1,6:10] (the only slice `predict` consumes, :295);
+ * time_idx [T].  r_pred_out [T-1,7].  Block outputs (all nullable together via Phi_out==NULL):
+ *   Phi_out [T-1,6,6]   state-transition matrix of pair i in [p,v] order; the reference's dense Jf has
+ *                       pair block [D Phi_i | -D], D = diag(1,1,1,vel_coeff x3), rot columns zero
+ *   qgrad_out [T,3], Hq_diag_out [T,3,3], Hq_off_out [T-1,3,3] (= Hq[i,i+1]; Hq[i+1,i] is its transpose)
+ * x_pred_out [T,6] nullable: propagated [p,v] of every frame (pose_pred / vel_pred of the reference). */
+int vinsat_predict(vinsat_ctx* ctx, int mem, int64_t n_frames, const double* states, const double* cum_rot,
+                   const int64_t* time_idx, double quat_coeff, double vel_coeff, int mode,
+                   double* r_pred_out, double* x_pred_out, double* Phi_out, double* qgrad_out,
+                   double* Hq_diag_out, double* Hq_off_out);
+
+/* ---- a8: propagate_dynamics_init (BA/BA_utils.py:89-129) --------------------------------------
+ * One state chained for n_steps RK4 steps of dt (orbit) and n_steps quaternion increments exp(dt*omega_k).
+ * state0 [10] (velocity taken from vel0 [3], as the reference does), omega [n_steps,3].
+ * states_out [(n_steps+1),10] including the start row. */
+int vinsat_propagate_chain(vinsat_ctx* ctx, int mem, int64_t n_steps, double dt, const double* state0,
+                           const double* vel0, const double* omega, double* states_out);
+
+/* ---- a11: batched orbit simulation (trajgen_pipe.py:145-152 / sim/orbit_gen.py:145-152) ----------
+ * n_traj initial [p,v] states propagated n_steps RK4 steps of h; every `stride`-th state is stored:
+ * out [n_traj, n_steps/stride + 1, 6]. */
+int vinsat_orbit_propagate(vinsat_ctx* ctx, int mem, int64_t n_traj, int64_t n_steps, int64_t stride, double h,
+                           const double* x0, double* out);
+
+/* ---- batched BA / OD (BA/BA_filtering.py:4-98 driven by od_pipe.py:1036-1040) -----------------------
+ * A batch holds P independent problems, concatenated; problem p owns frames
+ * [frame_off[p], frame_off[p+1]) and observations [obs_off[p], obs_off[p+1]).  `ii` holds frame indices
+ * LOCAL to the problem and must be non-decreasing inside each problem (read_detections builds it that
+ * way, od_pipe.py:214-228); the Python mirror sorts otherwise. */
+typedef struct {
+  int64_t n_problems;
+  const int64_t* frame_off;     /* [P+1] */
+  const int64_t* obs_off;       /* [P+1] */
+  const double* states;         /* [Ttot,10] initial guess */
+  const double* intrinsics;     /* [Ttot,4]  */
+  const double* cum_rot;        /* [Ttot,4]  */
+  const int64_t* time_idx;      /* [Ttot]    */
+  const double* landmarks_xyz;  /* [Mtot,3]  */
+  const double* landmarks_uv;   /* [Mtot,2]  */
+  const double* confidences;    /* [Mtot]    */
+  const int64_t* ii;            /* [Mtot]    */
+} vinsat_problem_desc;
+
+/* Allocates device storage for the sizes in `desc` and uploads it (host pointers). */
+int vinsat_batch_create(vinsat_ctx* ctx, const vinsat_problem_desc* desc, vinsat_batch** out);
+/* Re-upload new data of the SAME sizes (async on the context stream; host buffers should be pinned). */
+int vinsat_batch_upload(vinsat_batch* b, const vinsat_problem_desc* desc);
+int vinsat_batch_set_states(vinsat_batch* b, int mem, const double* states /* [Ttot,10] */);
+int vinsat_batch_get_states(vinsat_batch* b, int mem, double* states_out /* [Ttot,10] */);
+int vinsat_batch_destroy(vinsat_batch* b);
+
+/* One BA() call per problem (BA_filtering.py:4-98): residuals + Jacobians, robust weights, block
+ * tridiagonal normal equations, LM trials until accepted or lamda > 1e4, retraction.
+ * lamda_io [P] host: in = lamda_init, out = lamda_init for the next call (:79).  ntrials_out [P] nullable. */
+int vinsat_batch_ba_iterate(vinsat_batch* b, int iter, int initialize, int mode, double* lamda_io,
+                            int32_t* ntrials_out);
+/* streaming_version's schedule on one window (od_pipe.py:918,1036-1040): num_iters BA iterations, the first
+ * n_init with initialize=1.  Equivalent to calling vinsat_batch_ba_iterate in a loop. */
+int vinsat_batch_od_solve(vinsat_batch* b, int num_iters, int n_init, double lamda_init, int mode);
+/* JTwJ[:, -9:, -9:] of the last trial of the last iteration (BA_filtering.py:97).  out [P,9,9]. */
+int vinsat_batch_last_hessian(vinsat_batch* b, double* out);
+
+/* Per-iteration diagnostics of the LAST vinsat_batch_ba_iterate call, for parity tests (host outputs,
+ * any may be NULL): r_obs [Mtot,2], weights [Mtot] (after /max and *conf), c_obs [P], D [Ttot,9,9] (without
+ * damping), U [Ttot,9,9] (block (i,i+1); last of each problem unused), rhs [Ttot,9], dpose [Ttot,9]. */
+int vinsat_batch_debug_fetch(vinsat_batch* b, double* r_obs, double* weights, double* c_obs, double* D,
+                             double* U, double* rhs, double* dpose);
+
+/* Headline kernel, timed alone: residual + Jacobian for every resident observation (a1, unfused).
+ * Outputs stay on the device in SoA form (r[2][M], J[12][M]); `fetch` copies them out as
+ * r_out [Mtot,2], J_out [Mtot,2,6] (nonzero columns only), both nullable. */
+int vinsat_batch_eval_resjac(vinsat_batch* b);
+int vinsat_batch_fetch_resjac(vinsat_batch* b, double* r_out, double* J_out);
+
+/* Device-time of the library's kernels since the last reset, by kernel family, measured with CUDA
+ * events on the context stream (only when profiling is enabled; adds a sync per launch).  */
+int vinsat_ctx_enable_timing(vinsat_ctx* ctx, int on);
+int vinsat_ctx_reset_timing(vinsat_ctx* ctx);
+/* names_out: up to `cap` pointers to static strings; ms_out/launches_out parallel arrays. Returns count. */
+int vinsat_ctx_get_timing(vinsat_ctx* ctx, int cap, const char** names_out, double* ms_out, int64_t* launches_out);
+/* Total kernel launches issued by this context since creation (bench.py's `gpu_launches`). */
+int64_t vinsat_ctx_launch_count(const vinsat_ctx* ctx);
+
+/* ---- a10: SatCam batched projection / visibility (sim/SatCam.py:87-92,125-154,175-262) -------------
+ * poses [P,12] = [ECEF pos (m), dir, up, right] (SatCam.py:23-28; note up is negated, :52,81);
+ * landmarks_ecef [L,3] (m).  uv_out [P,L,2] nullable; inframe_out [P,L] uint8 nullable
+ * (0<=u<w_px, 0<=v<h_px, in front of the camera); count_out [P] int32 nullable (# in frame). */
+int vinsat_satcam_project(vinsat_ctx* ctx, int mem, int64_t n_poses, int64_t n_landmarks, const double* poses,
+                          const double* landmarks_ecef, double hfov_deg, int32_t w_px, int32_t h_px,
+                          double* uv_out, uint8_t* inframe_out, int32_t* count_out);
+/* Footprint corners by ray casting to the WGS84 ellipsoid (SatCam.py:94-147): corners_out [P,4,3] ECEF m
+ * (tl,tr,br,bl), hit_out [P,4] uint8. */
+int vinsat_satcam_corners(vinsat_ctx* ctx, int mem, int64_t n_poses, const double* poses, double hfov_deg,
+                          int32_t w_px, int32_t h_px, double* corners_out, uint8_t* hit_out);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* FP64 FMA peak of the device (DFMA microbenchmark), TFLOP/s; and a device copy bandwidth, GB/s. */
+int vinsat_measure_fp64_peak(vinsat_ctx* ctx, double* tflops_out);
+int vinsat_measure_copy_bw(vinsat_ctx* ctx, int64_t bytes, double* gbs_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VINSAT_B200_H */

@@ -1,0 +1,348 @@
+"""ctypes binding of ``libvinsat_b200.so`` (C ABI: ``include/vinsat_b200.h``).
+
+There is NO CPU fallback: if the shared library is missing, or no CUDA device is usable, every
+operator raises ``VinsatError``.  PyTorch is not needed here; tensors are handed over as raw
+pointers by the mirror modules (``BA/``, ``od_pipe.py`` ...).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvinsat_b200.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+MODE_STEP1S, MODE_SKIP100 = 0, 1
+
+c_dp = C.POINTER(C.c_double)
+c_i64p = C.POINTER(C.c_int64)
+c_i32p = C.POINTER(C.c_int32)
+c_u8p = C.POINTER(C.c_uint8)
+
+
+class VinsatError(RuntimeError):
+    pass
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [("n_problems", C.c_int64), ("frame_off", c_i64p), ("obs_off", c_i64p), ("states", c_dp),
+                ("intrinsics", c_dp), ("cum_rot", c_dp), ("time_idx", c_i64p), ("landmarks_xyz", c_dp),
+                ("landmarks_uv", c_dp), ("confidences", c_dp), ("ii", c_i64p)]
+
+
+# name -> (restype, argtypes); every function declared in include/vinsat_b200.h
+SIGNATURES = {
+    "vinsat_abi_version": (C.c_int, []),
+    "vinsat_device_count": (C.c_int, []),
+    "vinsat_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "vinsat_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "vinsat_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vinsat_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "vinsat_last_error": (C.c_char_p, [C.c_void_p]),
+    "vinsat_landmark_project": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_predict": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                 C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
+    "vinsat_propagate_chain": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "vinsat_orbit_propagate": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                                         C.c_void_p, C.c_void_p]),
+    "vinsat_batch_create": (C.c_int, [C.c_void_p, C.POINTER(ProblemDesc), C.POINTER(C.c_void_p)]),
+    "vinsat_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(ProblemDesc)]),
+    "vinsat_batch_set_states": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "vinsat_batch_get_states": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "vinsat_batch_destroy": (C.c_int, [C.c_void_p]),
+    "vinsat_batch_ba_iterate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "vinsat_batch_od_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int]),
+    "vinsat_batch_last_hessian": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vinsat_batch_debug_fetch": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7),
+    "vinsat_batch_eval_resjac": (C.c_int, [C.c_void_p]),
+    "vinsat_batch_fetch_resjac": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_ctx_enable_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "vinsat_ctx_reset_timing": (C.c_int, [C.c_void_p]),
+    "vinsat_ctx_get_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), c_dp, c_i64p]),
+    "vinsat_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "vinsat_satcam_project": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_satcam_corners": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_int32,
+                                        C.c_int32, C.c_void_p, C.c_void_p]),
+    "vinsat_measure_fp64_peak": (C.c_int, [C.c_void_p, c_dp]),
+    "vinsat_measure_copy_bw": (C.c_int, [C.c_void_p, C.c_int64, c_dp]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once).  Raises VinsatError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VinsatError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C vinsat_b200/csrc).  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError => ABI mismatch, fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vinsat_abi_version() != 1:
+        raise VinsatError("ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    """Raw pointer of a NumPy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+class Context:
+    """Owns a ``vinsat_ctx`` (device, stream, scratch)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.vinsat_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise VinsatError("vinsat_ctx_create(%d) failed (%d): %s" % (
+                device, rc, (self.lib.vinsat_last_error(None) or b"").decode()))
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise VinsatError("vinsat error %d: %s" % (rc, (self.lib.vinsat_last_error(self.h) or b"").decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vinsat_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self.check(self.lib.vinsat_ctx_synchronize(self.h))
+
+    def set_stream(self, cuda_stream):
+        self.check(self.lib.vinsat_ctx_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def launch_count(self):
+        return int(self.lib.vinsat_ctx_launch_count(self.h))
+
+    def enable_timing(self, on=True):
+        self.check(self.lib.vinsat_ctx_enable_timing(self.h, 1 if on else 0))
+
+    def reset_timing(self):
+        self.check(self.lib.vinsat_ctx_reset_timing(self.h))
+
+    def timing(self):
+        names = (C.c_char_p * 32)()
+        ms = (C.c_double * 32)()
+        n_l = (C.c_int64 * 32)()
+        n = self.lib.vinsat_ctx_get_timing(self.h, 32, names, ms, n_l)
+        return {names[i].decode(): (ms[i], n_l[i]) for i in range(n)}
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        self.check(self.lib.vinsat_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    def copy_bw_gbs(self, nbytes=1 << 30):
+        v = C.c_double()
+        self.check(self.lib.vinsat_measure_copy_bw(self.h, int(nbytes), C.byref(v)))
+        return v.value
+
+    # ---- stand-alone operators (host NumPy in / out) --------------------------------------------
+    def landmark_project(self, states, landmarks_xyz, intrinsics, ii, jacobian=True):
+        states, xyz, intr, ii = f64(states), f64(landmarks_xyz), f64(intrinsics), i64(ii)
+        T, M = states.shape[0], xyz.shape[0]
+        uv = np.empty((M, 2))
+        Jg = np.empty((M, 2, 9)) if jacobian else None
+        self.check(self.lib.vinsat_landmark_project(self.h, MEM_HOST, T, M, _ptr(states), _ptr(intr), _ptr(xyz),
+                                                    _ptr(ii), _ptr(uv), _ptr(Jg)))
+        return (uv, Jg) if jacobian else uv
+
+    def predict(self, states, cum_rot, time_idx, quat_coeff=100.0, vel_coeff=100.0, jacobian=True,
+                mode=MODE_STEP1S, want_x_pred=False):
+        states, cum_rot, time_idx = f64(states), f64(cum_rot), i64(time_idx)
+        T = states.shape[0]
+        out = {"r_pred": np.empty((T - 1, 7))}
+        if want_x_pred:
+            out["x_pred"] = np.empty((T, 6))
+        if jacobian:
+            out.update(Phi=np.empty((T - 1, 6, 6)), qgrad=np.empty((T, 3)), Hq_diag=np.empty((T, 3, 3)),
+                       Hq_off=np.empty((T - 1, 3, 3)))
+        self.check(self.lib.vinsat_predict(self.h, MEM_HOST, T, _ptr(states), _ptr(cum_rot), _ptr(time_idx),
+                                           float(quat_coeff), float(vel_coeff), int(mode), _ptr(out["r_pred"]),
+                                           _ptr(out.get("x_pred")), _ptr(out.get("Phi")), _ptr(out.get("qgrad")),
+                                           _ptr(out.get("Hq_diag")), _ptr(out.get("Hq_off"))))
+        return out
+
+    def propagate_chain(self, state0, vel0, omega, dt=1.0):
+        state0, vel0, omega = f64(state0), f64(vel0), f64(omega).reshape(-1, 3)
+        n = omega.shape[0]
+        out = np.empty((n + 1, 10))
+        self.check(self.lib.vinsat_propagate_chain(self.h, MEM_HOST, n, float(dt), _ptr(state0), _ptr(vel0),
+                                                   _ptr(omega), _ptr(out)))
+        return out
+
+    def orbit_propagate(self, x0, n_steps, stride=1, h=1.0):
+        x0 = f64(x0).reshape(-1, 6)
+        out = np.empty((x0.shape[0], n_steps // stride + 1, 6))
+        self.check(self.lib.vinsat_orbit_propagate(self.h, MEM_HOST, x0.shape[0], int(n_steps), int(stride),
+                                                   float(h), _ptr(x0), _ptr(out)))
+        return out
+
+    def satcam_project(self, poses, landmarks_ecef, hfov, w_px, h_px, want_uv=True, want_mask=True,
+                       want_count=True):
+        poses, lm = f64(poses).reshape(-1, 12), f64(landmarks_ecef).reshape(-1, 3)
+        P, L = poses.shape[0], lm.shape[0]
+        uv = np.empty((P, L, 2)) if want_uv else None
+        mask = np.empty((P, L), dtype=np.uint8) if want_mask else None
+        cnt = np.empty(P, dtype=np.int32) if want_count else None
+        self.check(self.lib.vinsat_satcam_project(self.h, MEM_HOST, P, L, _ptr(poses), _ptr(lm), float(hfov),
+                                                  int(w_px), int(h_px), _ptr(uv), _ptr(mask), _ptr(cnt)))
+        return uv, mask, cnt
+
+    def satcam_corners(self, poses, hfov, w_px, h_px):
+        poses = f64(poses).reshape(-1, 12)
+        P = poses.shape[0]
+        corners = np.empty((P, 4, 3))
+        hit = np.empty((P, 4), dtype=np.uint8)
+        self.check(self.lib.vinsat_satcam_corners(self.h, MEM_HOST, P, _ptr(poses), float(hfov), int(w_px),
+                                                  int(h_px), _ptr(corners), _ptr(hit)))
+        return corners, hit
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def concat_problems(problems):
+    """list of problem dicts (keys as vinsat_b200.synth) -> concatenated host arrays + offsets."""
+    frame_off = np.zeros(len(problems) + 1, dtype=np.int64)
+    obs_off = np.zeros(len(problems) + 1, dtype=np.int64)
+    for p, pr in enumerate(problems):
+        frame_off[p + 1] = frame_off[p] + pr["states0"].shape[0]
+        obs_off[p + 1] = obs_off[p] + pr["xyz"].shape[0]
+    cat = lambda k, dt: np.ascontiguousarray(np.concatenate([np.asarray(pr[k], dtype=dt) for pr in problems]))
+    return dict(frame_off=frame_off, obs_off=obs_off, states=cat("states0", np.float64),
+                intrinsics=cat("intr", np.float64), cum_rot=cat("cum_rot", np.float64),
+                time_idx=cat("time_idx", np.int64), landmarks_xyz=cat("xyz", np.float64),
+                landmarks_uv=cat("uv", np.float64), confidences=cat("conf", np.float64), ii=cat("ii", np.int64))
+
+
+class Batch:
+    """Device-resident batch of independent OD problems (``vinsat_batch``)."""
+
+    def __init__(self, ctx, arrays):
+        """arrays: dict as returned by concat_problems (NumPy or pinned torch tensors; kept alive here)."""
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.P = len(arrays["frame_off"]) - 1
+        self.frame_off = np.asarray(arrays["frame_off"]).copy()
+        self.obs_off = np.asarray(arrays["obs_off"]).copy()
+        self.T = int(self.frame_off[-1])
+        self.M = int(self.obs_off[-1])
+        self._desc = self._make_desc(arrays)
+        h = C.c_void_p()
+        ctx.check(self.lib.vinsat_batch_create(ctx.h, C.byref(self._desc), C.byref(h)))
+        self.h = h
+
+    def _make_desc(self, a):
+        self._keep = a
+        d = ProblemDesc()
+        d.n_problems = self.P
+        cast = lambda x, t: C.cast(_ptr(x), t)
+        d.frame_off = cast(a["frame_off"], c_i64p); d.obs_off = cast(a["obs_off"], c_i64p)
+        d.states = cast(a["states"], c_dp); d.intrinsics = cast(a["intrinsics"], c_dp)
+        d.cum_rot = cast(a["cum_rot"], c_dp); d.time_idx = cast(a["time_idx"], c_i64p)
+        d.landmarks_xyz = cast(a["landmarks_xyz"], c_dp); d.landmarks_uv = cast(a["landmarks_uv"], c_dp)
+        d.confidences = cast(a["confidences"], c_dp); d.ii = cast(a["ii"], c_i64p)
+        return d
+
+    def upload(self, arrays):
+        self._desc = self._make_desc(arrays)
+        self.ctx.check(self.lib.vinsat_batch_upload(self.h, C.byref(self._desc)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vinsat_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_states(self, states):
+        states = f64(states)
+        assert states.shape == (self.T, 10)
+        self.ctx.check(self.lib.vinsat_batch_set_states(self.h, MEM_HOST, _ptr(states)))
+
+    def get_states(self, out=None):
+        out = np.empty((self.T, 10)) if out is None else out
+        self.ctx.check(self.lib.vinsat_batch_get_states(self.h, MEM_HOST, _ptr(out)))
+        return out
+
+    def ba_iterate(self, it, lamda, initialize=False, mode=MODE_STEP1S):
+        lam = np.ascontiguousarray(np.broadcast_to(np.asarray(lamda, dtype=np.float64), (self.P,))).copy()
+        ntr = np.zeros(self.P, dtype=np.int32)
+        self.ctx.check(self.lib.vinsat_batch_ba_iterate(self.h, int(it), 1 if initialize else 0, int(mode),
+                                                        _ptr(lam), _ptr(ntr)))
+        return lam, ntr
+
+    def od_solve(self, num_iters=20, n_init=10, lamda_init=1e-4, mode=MODE_STEP1S):
+        self.ctx.check(self.lib.vinsat_batch_od_solve(self.h, int(num_iters), int(n_init), float(lamda_init),
+                                                      int(mode)))
+
+    def last_hessian(self):
+        out = np.empty((self.P, 9, 9))
+        self.ctx.check(self.lib.vinsat_batch_last_hessian(self.h, _ptr(out)))
+        return out
+
+    def debug_fetch(self):
+        T, M, P = self.T, self.M, self.P
+        out = dict(r_obs=np.empty((M, 2)), weights=np.empty(M), c_obs=np.empty(P), D=np.empty((T, 9, 9)),
+                   U=np.empty((T, 9, 9)), rhs=np.empty((T, 9)), dpose=np.empty((T, 9)))
+        self.ctx.check(self.lib.vinsat_batch_debug_fetch(self.h, *[_ptr(out[k]) for k in
+                                                                   ("r_obs", "weights", "c_obs", "D", "U", "rhs", "dpose")]))
+        return out
+
+    def eval_resjac(self):
+        self.ctx.check(self.lib.vinsat_batch_eval_resjac(self.h))
+
+    def fetch_resjac(self):
+        r = np.empty((self.M, 2))
+        J = np.empty((self.M, 2, 6))
+        self.ctx.check(self.lib.vinsat_batch_fetch_resjac(self.h, _ptr(r), _ptr(J)))
+        return r, J

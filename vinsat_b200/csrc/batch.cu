@@ -1,0 +1,374 @@
+// Device-resident batch of OD problems: allocation, upload, BA iteration schedule (host side of a5-a7).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "launch.h"
+
+using namespace vs;
+
+namespace {
+
+template <typename T>
+int dev_alloc(vinsat_ctx* ctx, T** p, int64_t n) {
+  if (n < 1) n = 1;
+  cudaError_t e = cudaMalloc((void**)p, (size_t)n * sizeof(T));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(ctx, VINSAT_ENOMEM, "cudaMalloc of %lld bytes failed: %s", (long long)(n * sizeof(T)),
+                     cudaGetErrorString(e));
+  }
+  return VINSAT_OK;
+}
+
+#define VS_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != VINSAT_OK) return _rc; \
+  } while (0)
+
+void free_all(vinsat_batch* b) {
+  void* ptrs[] = {b->st, b->st_new, b->intr, b->crot, b->gap, b->fprob, b->dyn_order, b->obs_start, b->grec, b->drec,
+                  b->srec, b->wrec, b->delta, b->e_obs, b->e_dyn, b->X, b->uv, b->conf, b->oframe, b->r, b->wu, b->J,
+                  b->d_frame_off, b->d_obs_off, b->c_obs, b->wmax, b->lam, b->lam_next, b->lam32_last, b->init_res,
+                  b->active, b->ntrials, b->sel_prefix, b->sel_rank, b->sel_hist, b->flags};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (b->h_flags) cudaFreeHost(b->h_flags);
+}
+
+int validate_desc(vinsat_ctx* ctx, const vinsat_problem_desc* d) {
+  VS_CHECK_ARG(ctx, d != nullptr);
+  VS_CHECK_ARG(ctx, d->n_problems >= 1);
+  VS_CHECK_ARG(ctx, d->frame_off && d->obs_off);
+  VS_CHECK_ARG(ctx, d->frame_off[0] == 0 && d->obs_off[0] == 0);
+  for (int64_t p = 0; p < d->n_problems; p++) {
+    VS_CHECK_ARG(ctx, d->frame_off[p + 1] >= d->frame_off[p]);
+    VS_CHECK_ARG(ctx, d->obs_off[p + 1] >= d->obs_off[p]);
+  }
+  const int64_t T = d->frame_off[d->n_problems], M = d->obs_off[d->n_problems];
+  VS_CHECK_ARG(ctx, T >= 1 && T < (1ll << 31) - 64 && M < (1ll << 31) - 64);
+  VS_CHECK_ARG(ctx, d->states && d->intrinsics && d->cum_rot && d->time_idx);
+  VS_CHECK_ARG(ctx, M == 0 || (d->landmarks_xyz && d->landmarks_uv && d->confidences && d->ii));
+  return VINSAT_OK;
+}
+
+// Frame-side indexing on the host (O(T)): gaps, problem ids, and the longest-gap-first pair order.
+int build_frame_index(vinsat_batch* b, const vinsat_problem_desc* d, std::vector<int32_t>& gap,
+                      std::vector<int32_t>& fprob, std::vector<int32_t>& order) {
+  vinsat_ctx* ctx = b->ctx;
+  const int64_t T = b->T;
+  gap.assign(T, 0);
+  fprob.assign(T, 0);
+  int32_t gmax = 0;
+  for (int64_t p = 0; p < b->P; p++) {
+    for (int64_t f = d->frame_off[p]; f < d->frame_off[p + 1]; f++) {
+      fprob[f] = (int32_t)p;
+      if (f + 1 < d->frame_off[p + 1]) {
+        const int64_t g = d->time_idx[f + 1] - d->time_idx[f];
+        if (g <= 0 || g > 100000000)
+          return set_error(ctx, VINSAT_EINVAL, "time_idx must be strictly increasing inside a problem (frame %lld)",
+                           (long long)f);
+        gap[f] = (int32_t)g;
+        gmax = std::max(gmax, gap[f]);
+      }
+    }
+  }
+  // counting sort by gap, descending (stable)
+  const int32_t nb = std::min<int32_t>(gmax, 1 << 20) + 1;
+  std::vector<int64_t> cnt(nb + 1, 0);
+  auto bucket = [&](int32_t g) { return std::min<int32_t>(g, nb - 1); };
+  int64_t np = 0;
+  for (int64_t f = 0; f < T; f++)
+    if (gap[f] > 0) { cnt[bucket(gap[f])]++; np++; }
+  std::vector<int64_t> start(nb + 1, 0);
+  int64_t run = 0;
+  for (int32_t g = nb - 1; g >= 0; g--) { start[g] = run; run += cnt[g]; }
+  order.assign(np, 0);
+  for (int64_t f = 0; f < T; f++)
+    if (gap[f] > 0) order[start[bucket(gap[f])]++] = (int32_t)f;
+  b->n_pairs = np;
+  return VINSAT_OK;
+}
+
+int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
+  vinsat_ctx* ctx = b->ctx;
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (d->n_problems != b->P || d->frame_off[d->n_problems] != b->T || d->obs_off[d->n_problems] != b->M)
+    return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_upload: sizes differ from the batch (P,T,M)");
+  cudaStream_t s = ctx->stream;
+  const int64_t P = b->P, T = b->T, M = b->M;
+  b->frame_off.assign(d->frame_off, d->frame_off + P + 1);
+  b->obs_off.assign(d->obs_off, d->obs_off + P + 1);
+  b->max_obs_per_problem = 0;
+  for (int64_t p = 0; p < P; p++) b->max_obs_per_problem = std::max(b->max_obs_per_problem, d->obs_off[p + 1] - d->obs_off[p]);
+  std::vector<int32_t> gap, fprob, order;
+  VS_TRY(build_frame_index(b, d, gap, fprob, order));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->d_frame_off, d->frame_off, (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->d_obs_off, d->obs_off, (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->gap, gap.data(), T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->fprob, fprob.data(), T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  if (b->n_pairs)
+    VS_CUDA(ctx, cudaMemcpyAsync(b->dyn_order, order.data(), b->n_pairs * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->st, d->states, T * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->intr, d->intrinsics, T * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->crot, d->cum_rot, T * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, 4 * sizeof(int32_t), s));
+  if (M > 0) {
+    // stage AoS observation arrays + ii in scratch, then transpose to SoA / index on the device
+    const size_t need = (size_t)M * (3 + 2) * sizeof(double) + (size_t)M * sizeof(int64_t);
+    char* sc = (char*)ctx_scratch(ctx, need);
+    if (!sc) return set_error(ctx, VINSAT_ENOMEM, "scratch allocation of %zu bytes failed", need);
+    double* sx = (double*)sc;
+    double* suv = sx + 3 * M;
+    int64_t* sii = (int64_t*)(suv + 2 * M);
+    VS_CUDA(ctx, cudaMemcpyAsync(sx, d->landmarks_xyz, M * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    VS_CUDA(ctx, cudaMemcpyAsync(suv, d->landmarks_uv, M * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    VS_CUDA(ctx, cudaMemcpyAsync(sii, d->ii, M * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    VS_CUDA(ctx, cudaMemcpyAsync(b->conf, d->confidences, M * sizeof(double), cudaMemcpyHostToDevice, s));
+    VS_TRY(launch_aos_to_soa(ctx, sx, b->X, M, 3));
+    VS_TRY(launch_aos_to_soa(ctx, suv, b->uv, M, 2));
+    VS_TRY(launch_obs_index(b, sii));
+  } else {
+    VS_TRY(launch_obs_index(b, nullptr));
+  }
+  VS_CUDA(ctx, cudaMemcpyAsync(b->h_flags, b->flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  VS_CUDA(ctx, cudaStreamSynchronize(s));
+  if (b->h_flags[1] & 1) return set_error(ctx, VINSAT_EINVAL, "ii out of range for its problem's frame count");
+  if (b->h_flags[1] & 2) return set_error(ctx, VINSAT_EINVAL, "ii must be non-decreasing inside each problem");
+  b->have_iter = false;
+  return VINSAT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vinsat_batch_create(vinsat_ctx* ctx, const vinsat_problem_desc* d, vinsat_batch** out) {
+  if (!ctx || !out) return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_create: NULL argument");
+  *out = nullptr;
+  VS_TRY(validate_desc(ctx, d));
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  vinsat_batch* b = new vinsat_batch();
+  b->ctx = ctx;
+  b->P = d->n_problems;
+  b->T = d->frame_off[b->P];
+  b->M = d->obs_off[b->P];
+  const int64_t P = b->P, T = b->T, M = b->M;
+  int rc = VINSAT_OK;
+#define A(ptr, n) if (rc == VINSAT_OK) rc = dev_alloc(ctx, &b->ptr, (n))
+  A(st, T * 10); A(st_new, T * 10); A(intr, T * 4); A(crot, T * 4); A(gap, T); A(fprob, T); A(dyn_order, T);
+  A(obs_start, T + 1); A(grec, T * VS_GREC); A(drec, T * VS_DREC); A(srec, T * VS_SREC); A(wrec, T * VS_WREC);
+  A(delta, T * 9); A(e_obs, T); A(e_dyn, T);
+  A(X, M * 3); A(uv, M * 2); A(conf, M); A(oframe, M); A(r, M * 2); A(wu, M);
+  A(d_frame_off, P + 1); A(d_obs_off, P + 1); A(c_obs, P); A(wmax, P); A(lam, P); A(lam_next, P); A(lam32_last, P);
+  A(init_res, P); A(active, P); A(ntrials, P); A(sel_prefix, P); A(sel_rank, P); A(sel_hist, P * 2048); A(flags, 4);
+#undef A
+  if (rc == VINSAT_OK && cudaMallocHost((void**)&b->h_flags, 4 * sizeof(int32_t)) != cudaSuccess) {
+    cudaGetLastError();
+    rc = set_error(ctx, VINSAT_ENOMEM, "cudaMallocHost failed");
+  }
+  if (rc == VINSAT_OK) {
+    cudaMemsetAsync(b->sel_hist, 0, (size_t)P * 2048 * sizeof(unsigned int), ctx->stream);
+    cudaMemsetAsync(b->e_obs, 0, (size_t)T * sizeof(double), ctx->stream);
+    cudaMemsetAsync(b->e_dyn, 0, (size_t)T * sizeof(double), ctx->stream);
+    cudaMemsetAsync(b->drec, 0, (size_t)T * VS_DREC * sizeof(double), ctx->stream);
+    rc = do_upload(b, d);
+  }
+  if (rc != VINSAT_OK) {
+    free_all(b);
+    delete b;
+    return rc;
+  }
+  *out = b;
+  return VINSAT_OK;
+}
+
+int vinsat_batch_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
+  if (!b) return set_error(nullptr, VINSAT_EINVAL, "vinsat_batch_upload: NULL batch");
+  VS_TRY(validate_desc(b->ctx, d));
+  return do_upload(b, d);
+}
+
+int vinsat_batch_destroy(vinsat_batch* b) {
+  if (!b) return VINSAT_OK;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  free_all(b);
+  delete b;
+  return VINSAT_OK;
+}
+
+int vinsat_batch_set_states(vinsat_batch* b, int mem, const double* states) {
+  if (!b || !states) return set_error(b ? b->ctx : nullptr, VINSAT_EINVAL, "vinsat_batch_set_states: NULL argument");
+  vinsat_ctx* ctx = b->ctx;
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->st, states, b->T * 10 * sizeof(double),
+                               mem == VINSAT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                               ctx->stream));
+  if (mem != VINSAT_MEM_DEVICE) VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VINSAT_OK;
+}
+
+int vinsat_batch_get_states(vinsat_batch* b, int mem, double* states_out) {
+  if (!b || !states_out) return set_error(b ? b->ctx : nullptr, VINSAT_EINVAL, "vinsat_batch_get_states: NULL argument");
+  vinsat_ctx* ctx = b->ctx;
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  VS_CUDA(ctx, cudaMemcpyAsync(states_out, b->st, b->T * 10 * sizeof(double),
+                               mem == VINSAT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                               ctx->stream));
+  VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VINSAT_OK;
+}
+
+// One BA() call for every problem of the batch; lam_dev_in holds lamda_init per problem on the device.
+static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode, const double* lam_dev_in) {
+  vinsat_ctx* ctx = b->ctx;
+  const double quat_coeff = 100.0, vel_coeff = 100.0;                                  // BA_filtering.py:11-12
+  const double alpha = std::min(std::max(1.0 - (2.0 * ((double)iter / 5.0) - 1.0), 1.0), 2.0);   // :22
+  const double it1 = (double)iter + 1.0;
+  const double Sigma = std::min(10000.0 * it1 * it1, 1000000.0);                       // :26
+  VS_TRY(launch_obs_residual(b));
+  VS_TRY(launch_select_median(b));
+  VS_TRY(launch_obs_assemble(b, alpha));
+  if (!initialize) {
+    VS_TRY(launch_dynamics_stm(ctx, b->n_pairs, b->dyn_order, b->st, b->gap, vel_coeff, mode, b->drec, nullptr));
+    VS_TRY(launch_quat_terms(ctx, b->T, b->st, b->crot, b->gap, quat_coeff, b->drec));
+  }
+  VS_TRY(launch_system_build(b, initialize, Sigma, vel_coeff));
+  VS_TRY(launch_init_residual(b, initialize, Sigma, 0.0, lam_dev_in));
+  for (int trial = 0; trial < 16; trial++) {
+    VS_TRY(launch_solve_retract(b));
+    VS_TRY(launch_obs_trial(b));
+    if (!initialize)
+      VS_TRY(launch_dyn_trial(ctx, b->n_pairs, b->dyn_order, b->st_new, b->crot, b->gap, b->active, b->fprob,
+                              quat_coeff, vel_coeff, mode, b->e_dyn, nullptr));
+    VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, sizeof(int32_t), ctx->stream));
+    VS_TRY(launch_accept(b, initialize, Sigma));
+    VS_CUDA(ctx, cudaMemcpyAsync(b->h_flags, b->flags, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (b->h_flags[0] == 0) break;
+  }
+  std::swap(b->st, b->st_new);     // every problem's last trial is returned, accepted or not (:60,98)
+  b->have_iter = true;
+  b->last_initialize = initialize;
+  return VINSAT_OK;
+}
+
+int vinsat_batch_ba_iterate(vinsat_batch* b, int iter, int initialize, int mode, double* lamda_io,
+                            int32_t* ntrials_out) {
+  if (!b || !lamda_io) return set_error(b ? b->ctx : nullptr, VINSAT_EINVAL, "vinsat_batch_ba_iterate: NULL argument");
+  vinsat_ctx* ctx = b->ctx;
+  VS_CHECK_ARG(ctx, mode == VINSAT_MODE_STEP1S || mode == VINSAT_MODE_SKIP100);
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->lam_next, lamda_io, b->P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  VS_TRY(ba_iterate_device(b, iter, initialize, mode, b->lam_next));
+  VS_CUDA(ctx, cudaMemcpyAsync(lamda_io, b->lam_next, b->P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ntrials_out)
+    VS_CUDA(ctx, cudaMemcpyAsync(ntrials_out, b->ntrials, b->P * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VINSAT_OK;
+}
+
+int vinsat_batch_od_solve(vinsat_batch* b, int num_iters, int n_init, double lamda_init, int mode) {
+  if (!b) return set_error(nullptr, VINSAT_EINVAL, "vinsat_batch_od_solve: NULL batch");
+  vinsat_ctx* ctx = b->ctx;
+  VS_CHECK_ARG(ctx, mode == VINSAT_MODE_STEP1S || mode == VINSAT_MODE_SKIP100);
+  VS_CHECK_ARG(ctx, num_iters >= 0);
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  double* h = (double*)ctx_pinned(ctx, b->P * sizeof(double));
+  if (!h) return set_error(ctx, VINSAT_ENOMEM, "pinned scratch failed");
+  for (int64_t p = 0; p < b->P; p++) h[p] = lamda_init;
+  VS_CUDA(ctx, cudaMemcpyAsync(b->lam_next, h, b->P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  for (int it = 0; it < num_iters; it++) VS_TRY(ba_iterate_device(b, it, it < n_init ? 1 : 0, mode, b->lam_next));
+  return VINSAT_OK;
+}
+
+int vinsat_batch_last_hessian(vinsat_batch* b, double* out) {
+  if (!b || !out) return set_error(b ? b->ctx : nullptr, VINSAT_EINVAL, "vinsat_batch_last_hessian: NULL argument");
+  vinsat_ctx* ctx = b->ctx;
+  if (!b->have_iter) return set_error(ctx, VINSAT_EINVAL, "no BA iteration has run on this batch");
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<double> l32(b->P);
+  VS_CUDA(ctx, cudaMemcpyAsync(l32.data(), b->lam32_last, b->P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  for (int64_t p = 0; p < b->P; p++) {
+    const int64_t fl = b->frame_off[p + 1] - 1;
+    if (fl < b->frame_off[p]) { memset(out + p * 81, 0, 81 * sizeof(double)); continue; }
+    VS_CUDA(ctx, cudaMemcpyAsync(out + p * 81, b->srec + fl * VS_SREC, 81 * sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+  }
+  VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int64_t p = 0; p < b->P; p++)
+    for (int k = 0; k < 9; k++) out[p * 81 + k * 10] += l32[p];      // JTwJ includes eye*lamda (:54,97)
+  return VINSAT_OK;
+}
+
+int vinsat_batch_debug_fetch(vinsat_batch* b, double* r_obs, double* weights, double* c_obs, double* D, double* U,
+                             double* rhs, double* dpose) {
+  if (!b) return set_error(nullptr, VINSAT_EINVAL, "vinsat_batch_debug_fetch: NULL batch");
+  vinsat_ctx* ctx = b->ctx;
+  if (!b->have_iter) return set_error(ctx, VINSAT_EINVAL, "no BA iteration has run on this batch");
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int64_t P = b->P, T = b->T, M = b->M;
+  if (r_obs && M) {
+    std::vector<double> soa(2 * M);
+    VS_CUDA(ctx, cudaMemcpy(soa.data(), b->r, 2 * M * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < M; k++) { r_obs[2 * k] = soa[k]; r_obs[2 * k + 1] = soa[M + k]; }
+  }
+  if (c_obs) VS_CUDA(ctx, cudaMemcpy(c_obs, b->c_obs, P * sizeof(double), cudaMemcpyDeviceToHost));
+  if (weights && M) {
+    std::vector<unsigned long long> wm(P);
+    VS_CUDA(ctx, cudaMemcpy(weights, b->wu, M * sizeof(double), cudaMemcpyDeviceToHost));
+    VS_CUDA(ctx, cudaMemcpy(wm.data(), b->wmax, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int64_t p = 0; p < P; p++) {
+      double w;
+      memcpy(&w, &wm[p], 8);
+      for (int64_t k = b->obs_off[p]; k < b->obs_off[p + 1]; k++) weights[k] = weights[k] / w;
+    }
+  }
+  if (D || U || rhs) {
+    std::vector<double> rec((size_t)T * VS_SREC);
+    VS_CUDA(ctx, cudaMemcpy(rec.data(), b->srec, rec.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t f = 0; f < T; f++) {
+      if (D) memcpy(D + f * 81, &rec[f * VS_SREC], 81 * sizeof(double));
+      if (U) memcpy(U + f * 81, &rec[f * VS_SREC + 81], 81 * sizeof(double));
+      if (rhs) memcpy(rhs + f * 9, &rec[f * VS_SREC + 162], 9 * sizeof(double));
+    }
+  }
+  if (dpose) VS_CUDA(ctx, cudaMemcpy(dpose, b->delta, T * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+  return VINSAT_OK;
+}
+
+int vinsat_batch_eval_resjac(vinsat_batch* b) {
+  if (!b) return set_error(nullptr, VINSAT_EINVAL, "vinsat_batch_eval_resjac: NULL batch");
+  vinsat_ctx* ctx = b->ctx;
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!b->J) VS_TRY(dev_alloc(ctx, &b->J, b->M * 12));
+  return launch_resjac(b);
+}
+
+int vinsat_batch_fetch_resjac(vinsat_batch* b, double* r_out, double* J_out) {
+  if (!b) return set_error(nullptr, VINSAT_EINVAL, "vinsat_batch_fetch_resjac: NULL batch");
+  vinsat_ctx* ctx = b->ctx;
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t M = b->M;
+  if (M == 0) return VINSAT_OK;
+  if (!b->J) return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_eval_resjac has not run");
+  double* tmp = (double*)ctx_scratch(ctx, (size_t)M * 12 * sizeof(double));
+  if (!tmp) return set_error(ctx, VINSAT_ENOMEM, "scratch failed");
+  if (r_out) {
+    VS_TRY(launch_soa_to_aos(ctx, b->r, tmp, M, 2));
+    VS_CUDA(ctx, cudaMemcpyAsync(r_out, tmp, M * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  if (J_out) {
+    VS_TRY(launch_soa_to_aos(ctx, b->J, tmp, M, 12));
+    VS_CUDA(ctx, cudaMemcpyAsync(J_out, tmp, M * 12 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return VINSAT_OK;
+}
+
+}  // extern "C"

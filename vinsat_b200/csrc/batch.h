@@ -1,0 +1,60 @@
+// Device-resident batch of OD problems (internal).
+#pragma once
+#include "internal.h"
+
+// Per-frame record sizes (doubles).
+#define VS_GREC 28    // obs normal block: 21 sym (6x6 upper) + 6 rhs + 1 sum|r|
+#define VS_DREC 64    // dynamics: Phi 36 | r6 6 | rho 1 | qgrad 3 | Hq_diag 9 | Hq_off 9
+#define VS_SREC 172   // system: D 81 | U 81 | b 9 | pad 1
+#define VS_WREC 90    // solver: W = S^-1 U (col-major 81) | y 9
+
+struct vinsat_batch {
+  vinsat_ctx* ctx = nullptr;
+  int64_t P = 0, T = 0, M = 0;      // problems, total frames, total observations
+  int64_t n_pairs = 0;
+  int64_t max_obs_per_problem = 0;
+  // host copies of the offsets
+  std::vector<int64_t> frame_off, obs_off;
+  // ---- device, per frame ----
+  double* st = nullptr;        // [T][10] current states (AoS rows)
+  double* st_new = nullptr;    // [T][10] trial states
+  double* intr = nullptr;      // [T][4]
+  double* crot = nullptr;      // [T][4]
+  int32_t* gap = nullptr;      // [T] seconds to the next frame of the same problem, 0 = no pair
+  int32_t* fprob = nullptr;    // [T] problem of the frame
+  int32_t* dyn_order = nullptr;  // [n_pairs] frame index of each pair, longest gap first
+  int32_t* obs_start = nullptr;  // [T+1] CSR of observations by frame
+  double* grec = nullptr;      // [T][VS_GREC]
+  double* drec = nullptr;      // [T][VS_DREC]
+  double* srec = nullptr;      // [T][VS_SREC]
+  double* wrec = nullptr;      // [T][VS_WREC]
+  double* delta = nullptr;     // [T][9]
+  double* e_obs = nullptr;     // [T] trial partial sums (obs part)
+  double* e_dyn = nullptr;     // [T] trial partial sums (dynamics part)
+  // ---- device, per observation (SoA) ----
+  double* X = nullptr;         // [3][M]
+  double* uv = nullptr;        // [2][M]
+  double* conf = nullptr;      // [M]
+  int32_t* oframe = nullptr;   // [M] global frame of the observation
+  double* r = nullptr;         // [2][M] residuals
+  double* wu = nullptr;        // [M] conf * w_raw (un-normalised robust weight)
+  double* J = nullptr;         // [12][M] headline kernel output (allocated on first use)
+  // ---- device, per problem ----
+  int64_t* d_frame_off = nullptr;  // [P+1]
+  int64_t* d_obs_off = nullptr;    // [P+1]
+  double* c_obs = nullptr;     // [P] robust scale (lower median of |r|)
+  unsigned long long* wmax = nullptr;   // [P] bits of max w_raw
+  double* lam = nullptr;       // [P] current damping
+  double* lam_next = nullptr;  // [P] lamda_init for the next BA call
+  double* lam32_last = nullptr;  // [P] damping actually added in the last trial
+  double* init_res = nullptr;  // [P]
+  int32_t* active = nullptr;   // [P]
+  int32_t* ntrials = nullptr;  // [P]
+  unsigned long long* sel_prefix = nullptr;  // [P]
+  unsigned long long* sel_rank = nullptr;    // [P]
+  unsigned int* sel_hist = nullptr;          // [P][2048]
+  int32_t* flags = nullptr;    // [4]: 0 = n_active, 1 = index error
+  int32_t* h_flags = nullptr;  // pinned mirror
+  bool have_iter = false;
+  int last_initialize = 0;
+};

@@ -1,0 +1,106 @@
+// Internal declarations shared by the translation units of libvinsat_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vinsat_b200.h"
+
+namespace vs {
+
+// Kernel families for the launch counter / per-family device timing.
+enum Family {
+  F_PROJECT = 0,      // a1 stand-alone + headline residual/Jacobian kernel
+  F_OBS_RESID,        // residuals for the robust scale
+  F_SELECT,           // radix select (median) + weights max
+  F_OBS_ASSEMBLE,     // fused projection + weights + per-frame JtWJ / JtWr
+  F_DYNAMICS,         // RK4 + STM + quaternion terms
+  F_SYSTEM,           // block-tridiagonal system build
+  F_SOLVE,            // block-tridiagonal LU solve
+  F_RETRACT,          // retraction
+  F_TRIAL,            // trial residual evaluation (obs + dynamics)
+  F_ACCEPT,           // per-problem reductions, LM accept test
+  F_LAYOUT,           // AoS<->SoA conversion, gathers
+  F_SIM,              // orbit propagation / chain
+  F_SATCAM,           // SatCam projection / visibility
+  F_PEAK,             // peak microbenchmarks
+  F_COUNT
+};
+extern const char* const kFamilyNames[F_COUNT];
+
+struct TimedLaunch { int family; cudaEvent_t e0, e1; };
+
+}  // namespace vs
+
+struct vinsat_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  bool timing = false;
+  double fam_ms[vs::F_COUNT] = {0};
+  int64_t fam_launches[vs::F_COUNT] = {0};
+  std::vector<vs::TimedLaunch> pending;
+  std::vector<cudaEvent_t> event_pool;
+  // scratch (grown on demand)
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+namespace vs {
+
+int set_error(vinsat_ctx* ctx, int code, const char* fmt, ...);
+void set_global_error(const char* msg);
+void timing_begin(vinsat_ctx* ctx, int family);
+void timing_end(vinsat_ctx* ctx);
+void timing_resolve(vinsat_ctx* ctx);
+void* ctx_scratch(vinsat_ctx* ctx, size_t bytes);   // device scratch, valid until the next call
+void* ctx_pinned(vinsat_ctx* ctx, size_t bytes);    // pinned host scratch
+
+#define VS_CUDA(ctx, expr)                                                                      \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return vs::set_error((ctx), VINSAT_ECUDA, "%s failed: %s (%s:%d)", #expr,                 \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                         \
+  } while (0)
+
+#define VS_CHECK_ARG(ctx, cond)                                                                 \
+  do {                                                                                          \
+    if (!(cond)) return vs::set_error((ctx), VINSAT_EINVAL, "invalid argument: %s", #cond);     \
+  } while (0)
+
+// Launch wrapper: counts the launch, optionally brackets it with events, checks the launch error.
+#define VS_LAUNCH(ctx, family, kernel, grid, block, smem, ...)                                  \
+  do {                                                                                          \
+    vs::timing_begin((ctx), (family));                                                          \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                            \
+    vs::timing_end((ctx));                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess)                                                                      \
+      return vs::set_error((ctx), VINSAT_ECUDA, "launch %s failed: %s (%s:%d)", #kernel,        \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                         \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// RAII device buffer for the stand-alone entry points.
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
+};
+
+// ---- launchers implemented in the .cu files (device pointers, run on ctx->stream) ----------------
+// layout.cu
+int launch_aos_to_soa(vinsat_ctx* ctx, const double* aos, double* soa, int64_t n, int ncol, int64_t soa_stride);
+int launch_soa_to_aos(vinsat_ctx* ctx, const double* soa, double* aos, int64_t n, int ncol, int64_t soa_stride);
+
+}  // namespace vs

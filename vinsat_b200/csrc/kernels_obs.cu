@@ -1,0 +1,357 @@
+// Observation-side kernels (a1, a5, a6 of SURVEY.md section 8): pinhole projection of landmarks, closed-form
+// Jacobian, robust weights, and the segmented (per-frame) reduction of J^T W J / J^T W r.
+//
+// Layout: observations are SoA (X[3][M], uv[2][M], conf[M], oframe[M]) sorted by frame, so a warp reads
+// 32 consecutive doubles per array (fully coalesced 256 B requests); per-frame data (state row 80 B,
+// intrinsics 32 B) is AoS and is broadcast-read by the lanes that share a frame (L1 hits).
+#include "common.cuh"
+#include "launch.h"
+
+namespace vs {
+
+// ---------------------------------------------------------------------------------------------------------
+// layout conversion through shared memory: both sides coalesced
+// ---------------------------------------------------------------------------------------------------------
+template <int NCOL>
+__global__ void __launch_bounds__(256) k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int64_t n) {
+  __shared__ double tile[256 * NCOL];
+  const int64_t row0 = (int64_t)blockIdx.x * 256;
+  const int64_t rows = min((int64_t)256, n - row0);
+  const double* src = aos + row0 * NCOL;
+  for (int i = threadIdx.x; i < rows * NCOL; i += 256) tile[i] = src[i];
+  __syncthreads();
+  if (threadIdx.x < rows) {
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) soa[(int64_t)c * n + row0 + threadIdx.x] = tile[threadIdx.x * NCOL + c];
+  }
+}
+
+template <int NCOL>
+__global__ void __launch_bounds__(256) k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int64_t n) {
+  __shared__ double tile[256 * NCOL];
+  const int64_t row0 = (int64_t)blockIdx.x * 256;
+  const int64_t rows = min((int64_t)256, n - row0);
+  if (threadIdx.x < rows) {
+#pragma unroll
+    for (int c = 0; c < NCOL; c++) tile[threadIdx.x * NCOL + c] = soa[(int64_t)c * n + row0 + threadIdx.x];
+  }
+  __syncthreads();
+  double* dst = aos + row0 * NCOL;
+  for (int i = threadIdx.x; i < rows * NCOL; i += 256) dst[i] = tile[i];
+}
+
+int launch_aos_to_soa(vinsat_ctx* ctx, const double* aos, double* soa, int64_t n, int ncol) {
+  if (n == 0) return VINSAT_OK;
+  const int64_t grid = ceil_div(n, 256);
+  switch (ncol) {
+    case 1: VS_CUDA(ctx, cudaMemcpyAsync(soa, aos, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)); break;
+    case 2: VS_LAUNCH(ctx, F_LAYOUT, k_aos_to_soa<2>, grid, 256, 0, aos, soa, n); break;
+    case 3: VS_LAUNCH(ctx, F_LAYOUT, k_aos_to_soa<3>, grid, 256, 0, aos, soa, n); break;
+    case 6: VS_LAUNCH(ctx, F_LAYOUT, k_aos_to_soa<6>, grid, 256, 0, aos, soa, n); break;
+    case 12: VS_LAUNCH(ctx, F_LAYOUT, k_aos_to_soa<12>, grid, 256, 0, aos, soa, n); break;
+    default: return set_error(ctx, VINSAT_EINVAL, "aos_to_soa: unsupported ncol %d", ncol);
+  }
+  return VINSAT_OK;
+}
+
+int launch_soa_to_aos(vinsat_ctx* ctx, const double* soa, double* aos, int64_t n, int ncol) {
+  if (n == 0) return VINSAT_OK;
+  const int64_t grid = ceil_div(n, 256);
+  switch (ncol) {
+    case 1: VS_CUDA(ctx, cudaMemcpyAsync(aos, soa, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream)); break;
+    case 2: VS_LAUNCH(ctx, F_LAYOUT, k_soa_to_aos<2>, grid, 256, 0, soa, aos, n); break;
+    case 3: VS_LAUNCH(ctx, F_LAYOUT, k_soa_to_aos<3>, grid, 256, 0, soa, aos, n); break;
+    case 6: VS_LAUNCH(ctx, F_LAYOUT, k_soa_to_aos<6>, grid, 256, 0, soa, aos, n); break;
+    case 12: VS_LAUNCH(ctx, F_LAYOUT, k_soa_to_aos<12>, grid, 256, 0, soa, aos, n); break;
+    default: return set_error(ctx, VINSAT_EINVAL, "soa_to_aos: unsupported ncol %d", ncol);
+  }
+  return VINSAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// observation indexing: global frame of each observation, CSR by frame, sortedness check
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_problem(const int64_t* __restrict__ off, int P, int64_t k) {
+  int lo = 0, hi = P;   // off[lo] <= k < off[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= k) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) k_obs_index(int64_t M, int64_t T, int P, const int64_t* __restrict__ obs_off,
+                                                   const int64_t* __restrict__ frame_off,
+                                                   const int64_t* __restrict__ ii_local, int32_t* __restrict__ oframe,
+                                                   int32_t* __restrict__ obs_start, int32_t* __restrict__ flags) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= M) return;
+  const int p = find_problem(obs_off, P, k);
+  const int64_t nf = frame_off[p + 1] - frame_off[p];
+  const int64_t il = ii_local[k];
+  if (il < 0 || il >= nf) { atomicOr(&flags[1], 1); return; }
+  const int64_t f = frame_off[p] + il;
+  oframe[k] = (int32_t)f;
+  int64_t prev = -1;
+  if (k > 0) {
+    const int pp = find_problem(obs_off, P, k - 1);
+    prev = frame_off[pp] + ii_local[k - 1];
+  }
+  if (f < prev) { atomicOr(&flags[1], 2); return; }    // not sorted by frame
+  for (int64_t j = prev + 1; j <= f; j++) obs_start[j] = (int32_t)k;
+  if (k == M - 1)
+    for (int64_t j = f + 1; j <= T; j++) obs_start[j] = (int32_t)M;
+}
+
+int launch_obs_index(vinsat_batch* b, const int64_t* d_ii_local) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->M == 0) {
+    VS_CUDA(ctx, cudaMemsetAsync(b->obs_start, 0, (b->T + 1) * sizeof(int32_t), ctx->stream));
+    return VINSAT_OK;
+  }
+  VS_LAUNCH(ctx, F_LAYOUT, k_obs_index, ceil_div(b->M, 256), 256, 0, b->M, b->T, (int)b->P, b->d_obs_off,
+            b->d_frame_off, d_ii_local, b->oframe, b->obs_start, b->flags);
+  return VINSAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// a1 stand-alone, reference (AoS) layout, arbitrary ii
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_project_aos(int64_t T, int64_t M, const double* __restrict__ states,
+                                                     const double* __restrict__ intr, const double* __restrict__ xyz,
+                                                     const int64_t* __restrict__ ii, double* __restrict__ uv_out,
+                                                     double* __restrict__ Jg_out, int32_t* __restrict__ err) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= M) return;
+  const int64_t f = ii[k];
+  if (f < 0 || f >= T) { atomicOr(err, 1); return; }
+  const double* s = states + f * 10;
+  const double* c = intr + f * 4;
+  Quat q = {s[3], s[4], s[5], s[6]};
+  const double fx = c[0], fy = c[1];
+  ProjOut o = project_exact(s[0], s[1], s[2], q, xyz[k * 3 + 0], xyz[k * 3 + 1], xyz[k * 3 + 2], fx, fy, c[2], c[3]);
+  uv_out[k * 2 + 0] = o.u;
+  uv_out[k * 2 + 1] = o.v;
+  if (Jg_out) {
+    double ju[6], jv[6];
+    project_jacobian(o, fx, fy, ju, jv);
+    double* J = Jg_out + k * 18;
+#pragma unroll
+    for (int a = 0; a < 6; a++) { J[a] = ju[a]; J[9 + a] = jv[a]; }
+#pragma unroll
+    for (int a = 6; a < 9; a++) { J[a] = 0.0; J[9 + a] = 0.0; }
+  }
+}
+
+int launch_project_aos(vinsat_ctx* ctx, int64_t T, int64_t M, const double* states, const double* intr,
+                       const double* xyz, const int64_t* ii, double* uv_out, double* Jg_out, int32_t* err_flag) {
+  if (M == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_PROJECT, k_project_aos, ceil_div(M, 256), 256, 0, T, M, states, intr, xyz, ii, uv_out, Jg_out,
+            err_flag);
+  return VINSAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// headline kernel: residual + Jacobian, SoA in / SoA out (unfused a1)
+// Algorithmic bytes per observation: read X 24 + uv 16 + frame id 4, write r 16 + J (2x6 nonzeros) 96
+// = 156 B, plus the frame's state row / intrinsics (88 B) amortised over its observations.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resjac(int64_t M, const double* __restrict__ X, const double* __restrict__ uv,
+                                                const int32_t* __restrict__ oframe, const double* __restrict__ st,
+                                                const double* __restrict__ intr, double* __restrict__ r,
+                                                double* __restrict__ J) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= M) return;
+  const int f = oframe[k];
+  const double x = X[k], y = X[M + k], z = X[2 * M + k];
+  const double mu = uv[k], mv = uv[M + k];
+  const double* s = st + (int64_t)f * 10;
+  const double4 c = *reinterpret_cast<const double4*>(intr + (int64_t)f * 4);
+  Quat q = {s[3], s[4], s[5], s[6]};
+  ProjOut o = project_exact(s[0], s[1], s[2], q, x, y, z, c.x, c.y, c.z, c.w);
+  double ju[6], jv[6];
+  project_jacobian(o, c.x, c.y, ju, jv);
+  r[k] = xsub(mu, o.u);
+  r[M + k] = xsub(mv, o.v);
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    J[(int64_t)a * M + k] = ju[a];
+    J[(int64_t)(6 + a) * M + k] = jv[a];
+  }
+}
+
+int launch_resjac(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->M == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_PROJECT, k_resjac, ceil_div(b->M, 256), 256, 0, b->M, b->X, b->uv, b->oframe, b->st, b->intr,
+            b->r, b->J);
+  return VINSAT_OK;
+}
+
+// r = uv - project(st): input of the robust scale c = median |r| (BA_filtering.py:21,23)
+__global__ void __launch_bounds__(256) k_obs_residual(int64_t M, const double* __restrict__ X,
+                                                      const double* __restrict__ uv,
+                                                      const int32_t* __restrict__ oframe,
+                                                      const double* __restrict__ st, const double* __restrict__ intr,
+                                                      double* __restrict__ r) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= M) return;
+  const int f = oframe[k];
+  const double* s = st + (int64_t)f * 10;
+  const double4 c = *reinterpret_cast<const double4*>(intr + (int64_t)f * 4);
+  Quat q = {s[3], s[4], s[5], s[6]};
+  ProjOut o = project_exact(s[0], s[1], s[2], q, X[k], X[M + k], X[2 * M + k], c.x, c.y, c.z, c.w);
+  r[k] = xsub(uv[k], o.u);
+  r[M + k] = xsub(uv[M + k], o.v);
+}
+
+int launch_obs_residual(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->M == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_OBS_RESID, k_obs_residual, ceil_div(b->M, 256), 256, 0, b->M, b->X, b->uv, b->oframe, b->st,
+            b->intr, b->r);
+  return VINSAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused projection + Jacobian + robust weight + segmented reduction per frame (a1 + a5 + a6)
+// A group of 8 lanes owns one frame and strides over its observations; the 28 partial sums are combined
+// with xor-shuffles (fixed tree => deterministic) and written as one 224 B record.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGroup = 8;
+
+__device__ __forceinline__ double group_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+struct WeightParams {
+  double inv_am2;   // 1/|alpha-2| is NOT used: the reference divides, so keep |alpha-2| itself
+  double am2;       // |alpha - 2|
+  double ex;        // alpha/2 - 1
+  int alpha_is_two;
+};
+
+// BA_filtering.py:24, one component: ((r/c)^2/|alpha-2| + 1)^(alpha/2-1) / c^2
+__device__ __forceinline__ double robust_component(double r, double c, const WeightParams& wp) {
+  const double c2 = c * c;
+  if (wp.alpha_is_two) return 1.0 / c2;     // pow(inf|nan, 0) == 1 (IEEE / torch), SURVEY section 7
+  const double q = r / c;
+  return pow(q * q / wp.am2 + 1.0, wp.ex) / c2;
+}
+
+__global__ void __launch_bounds__(256) k_obs_assemble(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
+                                                      const int32_t* __restrict__ fprob,
+                                                      const double* __restrict__ X, const double* __restrict__ uv,
+                                                      const double* __restrict__ conf, const double* __restrict__ st,
+                                                      const double* __restrict__ intr,
+                                                      const double* __restrict__ c_obs, WeightParams wp,
+                                                      double* __restrict__ wu_out, double* __restrict__ grec,
+                                                      unsigned long long* __restrict__ wmax) {
+  const int gl = threadIdx.x & (kGroup - 1);
+  const int64_t f = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kGroup;
+  const bool valid = f < T;     // whole groups are valid or not; keep all lanes for the shuffles
+  double acc[VS_GREC];
+#pragma unroll
+  for (int i = 0; i < VS_GREC; i++) acc[i] = 0.0;
+  double wloc = 0.0;
+  int p = 0;
+  if (valid) {
+    const int k0 = obs_start[f], k1 = obs_start[f + 1];
+    if (k1 > k0) {
+      p = fprob[f];
+      const double c = c_obs[p];
+      const double* s = st + f * 10;
+      const double4 ci = *reinterpret_cast<const double4*>(intr + f * 4);
+      const double px = s[0], py = s[1], pz = s[2];
+      const Quat q = {s[3], s[4], s[5], s[6]};
+      for (int k = k0 + gl; k < k1; k += kGroup) {
+        ProjOut o = project_exact(px, py, pz, q, X[k], X[M + k], X[2 * M + k], ci.x, ci.y, ci.z, ci.w);
+        double ju[6], jv[6];
+        project_jacobian(o, ci.x, ci.y, ju, jv);
+        const double ru = xsub(uv[k], o.u), rv = xsub(uv[M + k], o.v);
+        const double wraw = 0.5 * (robust_component(ru, c, wp) + robust_component(rv, c, wp));
+        const double w = wraw * conf[k];
+        wu_out[k] = w;
+        wloc = fmax(wloc, wraw);
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+          const double wa_u = w * ju[a], wa_v = w * jv[a];
+#pragma unroll
+          for (int bcol = a; bcol < 6; bcol++) acc[idx++] += wa_u * ju[bcol] + wa_v * jv[bcol];
+          acc[21 + a] += wa_u * ru + wa_v * rv;
+        }
+        acc[27] += fabs(ru) + fabs(rv);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < VS_GREC; i++) acc[i] = group_sum(acc[i]);
+  wloc = fmax(wloc, __shfl_xor_sync(0xffffffffu, wloc, 4));
+  wloc = fmax(wloc, __shfl_xor_sync(0xffffffffu, wloc, 2));
+  wloc = fmax(wloc, __shfl_xor_sync(0xffffffffu, wloc, 1));
+  if (valid) {
+    double* g = grec + f * VS_GREC;
+#pragma unroll
+    for (int i = 0; i < VS_GREC; i++)
+      if ((i & (kGroup - 1)) == gl) g[i] = acc[i];
+    if (gl == 0 && wloc > 0.0) atomicMax(&wmax[p], (unsigned long long)__double_as_longlong(wloc));
+  }
+}
+
+int launch_obs_assemble(vinsat_batch* b, double alpha) {
+  vinsat_ctx* ctx = b->ctx;
+  WeightParams wp;
+  wp.am2 = fabs(alpha - 2.0);
+  wp.inv_am2 = 0.0;
+  wp.ex = alpha / 2.0 - 1.0;
+  wp.alpha_is_two = (wp.ex == 0.0) ? 1 : 0;
+  VS_CUDA(ctx, cudaMemsetAsync(b->wmax, 0, b->P * sizeof(unsigned long long), ctx->stream));
+  if (b->T == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble, ceil_div(b->T * kGroup, 256), 256, 0, b->T, b->M, b->obs_start,
+            b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
+  return VINSAT_OK;
+}
+
+// trial residual, observation part: e_obs[f] = sum_k wu_k (|ru| + |rv|) at st_new (BA_filtering.py:61,66)
+__global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
+                                                   const int32_t* __restrict__ fprob,
+                                                   const int32_t* __restrict__ active, const double* __restrict__ X,
+                                                   const double* __restrict__ uv, const double* __restrict__ wu,
+                                                   const double* __restrict__ st, const double* __restrict__ intr,
+                                                   double* __restrict__ e_obs) {
+  const int gl = threadIdx.x & (kGroup - 1);
+  const int64_t f = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kGroup;
+  const bool valid = f < T;
+  double e = 0.0;
+  bool live = false;
+  if (valid) {
+    live = active[fprob[f]] != 0;
+    const int k0 = obs_start[f], k1 = obs_start[f + 1];
+    if (live && k1 > k0) {
+      const double* s = st + f * 10;
+      const double4 ci = *reinterpret_cast<const double4*>(intr + f * 4);
+      const Quat q = {s[3], s[4], s[5], s[6]};
+      for (int k = k0 + gl; k < k1; k += kGroup) {
+        ProjOut o = project_exact(s[0], s[1], s[2], q, X[k], X[M + k], X[2 * M + k], ci.x, ci.y, ci.z, ci.w);
+        const double w = wu[k];
+        e += fabs(xsub(uv[k], o.u) * w) + fabs(xsub(uv[M + k], o.v) * w);
+      }
+    }
+  }
+  e = group_sum(e);
+  if (valid && live && gl == 0) e_obs[f] = e;
+}
+
+int launch_obs_trial(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->T == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_TRIAL, k_obs_trial, ceil_div(b->T * kGroup, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
+            b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs);
+  return VINSAT_OK;
+}
+
+}  // namespace vs

@@ -1,0 +1,444 @@
+// Per-problem kernels (a5 scale, a6 system build, a7 LM step of SURVEY.md section 8): exact lower-median by radix
+// select, block-tridiagonal normal equations, batched block LU solve with fused retraction, accept test.
+#include "common.cuh"
+#include "launch.h"
+
+namespace vs {
+
+// ---------------------------------------------------------------------------------------------------------
+// exact lower median of |r| per problem (torch.median semantics, BA_filtering.py:23): MSD radix select on
+// the bit pattern of the non-negative doubles, 11-bit digits, 6 passes.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSelBins = 2048;
+
+__global__ void k_select_init(int P, const int64_t* __restrict__ obs_off, unsigned long long* __restrict__ prefix,
+                              unsigned long long* __restrict__ rank) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const long long n = 2 * (obs_off[p + 1] - obs_off[p]);
+  prefix[p] = 0ull;
+  rank[p] = n > 0 ? (unsigned long long)((n - 1) / 2) : 0ull;
+}
+
+__global__ void __launch_bounds__(256) k_select_hist(int64_t M, const int64_t* __restrict__ obs_off,
+                                                     const double* __restrict__ r,
+                                                     const unsigned long long* __restrict__ prefix, int shift,
+                                                     int nbits, unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[kSelBins];
+  const int p = blockIdx.y;
+  const int64_t k0 = obs_off[p], k1 = obs_off[p + 1];
+  const int64_t n = 2 * (k1 - k0);
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = blockIdx.x * per, i1 = min(n, i0 + per);
+  if (i0 >= i1) return;
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const unsigned long long pre = prefix[p];
+  const int hs = shift + nbits;
+  const unsigned int dmask = (1u << nbits) - 1u;
+  const int64_t Mp = k1 - k0;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    // element i of the problem's 2*Mp values: component i / Mp, observation k0 + i % Mp
+    const int64_t comp = i >= Mp ? 1 : 0;
+    const double v = fabs(r[comp * M + k0 + (i - comp * Mp)]);
+    const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+    const bool match = hs >= 64 ? true : ((key >> hs) == (pre >> hs));
+    if (match) atomicAdd(&sh[(unsigned int)(key >> shift) & dmask], 1u);
+  }
+  __syncthreads();
+  unsigned int* g = hist + (int64_t)p * kSelBins;
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
+    if (sh[i]) atomicAdd(&g[i], sh[i]);
+}
+
+__global__ void __launch_bounds__(256) k_select_pick(unsigned long long* __restrict__ prefix,
+                                                     unsigned long long* __restrict__ rank, int shift,
+                                                     unsigned int* __restrict__ hist, int last,
+                                                     double* __restrict__ c_obs, const int64_t* __restrict__ obs_off) {
+  __shared__ unsigned int part[256];
+  const int p = blockIdx.x;
+  unsigned int* g = hist + (int64_t)p * kSelBins;
+  unsigned int loc[8];
+  unsigned int s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { loc[i] = g[threadIdx.x * 8 + i]; s += loc[i]; g[threadIdx.x * 8 + i] = 0; }
+  part[threadIdx.x] = s;
+  __syncthreads();
+  // exclusive prefix of the 256 partial sums (small; done redundantly by every thread's own walk)
+  unsigned long long before = 0;
+  for (int i = 0; i < threadIdx.x; i++) before += part[i];
+  const unsigned long long rk = rank[p];
+  __syncthreads();
+  if (rk >= before && rk < before + s) {
+    unsigned long long cum = before;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      if (rk < cum + loc[i]) {
+        const unsigned long long np = prefix[p] | ((unsigned long long)(threadIdx.x * 8 + i) << shift);
+        prefix[p] = np;
+        rank[p] = rk - cum;
+        if (last) c_obs[p] = __longlong_as_double((long long)np);
+        break;
+      }
+      cum += loc[i];
+    }
+  }
+  if (last && threadIdx.x == 0 && obs_off[p + 1] == obs_off[p]) c_obs[p] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+int launch_select_median(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->P == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_SELECT, k_select_init, ceil_div(b->P, 128), 128, 0, (int)b->P, b->d_obs_off, b->sel_prefix,
+            b->sel_rank);
+  const int shifts[6] = {53, 42, 31, 20, 9, 0};
+  const int nbits[6] = {11, 11, 11, 11, 11, 9};
+  int64_t chunks = ceil_div(2 * b->max_obs_per_problem, 256 * 16);
+  if (chunks < 1) chunks = 1;
+  const int64_t cap = std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / std::max<int64_t>(1, b->P));
+  if (chunks > cap) chunks = cap;
+  for (int pass = 0; pass < 6; pass++) {
+    dim3 grid((unsigned)chunks, (unsigned)b->P);
+    VS_LAUNCH(ctx, F_SELECT, k_select_hist, grid, 256, 0, b->M, b->d_obs_off, b->r, b->sel_prefix, shifts[pass],
+              nbits[pass], b->sel_hist);
+    VS_LAUNCH(ctx, F_SELECT, k_select_pick, (unsigned)b->P, 256, 0, b->sel_prefix, b->sel_rank, shifts[pass],
+              b->sel_hist, pass == 5 ? 1 : 0, b->c_obs, b->d_obs_off);
+  }
+  return VINSAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// block-tridiagonal normal equations (BA_filtering.py:28-48).  One warp per frame: the frame's
+// records are staged in shared memory, the 171 outputs are written as one contiguous record.
+// srec[f]: D 81 (row-major, WITHOUT damping) | U 81 (block (f,f+1), row-major) | b 9
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pv_index(int a) { return a < 3 ? a : (a >= 6 ? a - 3 : -1); }
+__device__ __forceinline__ int sym_index(int a, int b) {   // upper triangle of 6x6, a <= b
+  return a * 6 - (a * (a - 1)) / 2 + (b - a);
+}
+
+__global__ void __launch_bounds__(256) k_system(int64_t T, const int32_t* __restrict__ gap,
+                                                const int32_t* __restrict__ fprob,
+                                                const unsigned long long* __restrict__ wmax,
+                                                const double* __restrict__ grec, const double* __restrict__ drec,
+                                                int initialize, double Sigma, double vc,
+                                                double* __restrict__ srec) {
+  __shared__ double sm[8][VS_GREC + VS_DREC + 6];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t f = blockIdx.x * 8ll + warp;
+  if (f >= T) return;
+  double* G = sm[warp];
+  double* Dr = G + VS_GREC;
+  double* rp = Dr + VS_DREC;
+  const bool has_next = gap[f] > 0;
+  const bool has_prev = f > 0 && gap[f - 1] > 0;
+  if (lane < VS_GREC) G[lane] = grec[f * VS_GREC + lane];
+  if (!initialize) {
+    Dr[lane] = drec[f * VS_DREC + lane];
+    Dr[lane + 32] = drec[f * VS_DREC + lane + 32];
+    if (lane < 6) rp[lane] = has_prev ? drec[(f - 1) * VS_DREC + 36 + lane] : 0.0;
+  }
+  __syncwarp();
+  const unsigned long long wb = wmax[fprob[f]];
+  const double invw = wb ? 1.0 / __longlong_as_double((long long)wb) : 0.0;
+  const double dv[6] = {1.0, 1.0, 1.0, vc, vc, vc};
+  double* out = srec + f * VS_SREC;
+  for (int e = lane; e < 171; e += 32) {
+    double val = 0.0;
+    if (e < 81) {
+      const int a = e / 9, c = e % 9;
+      if (a < 6 && c < 6) val = invw * G[a <= c ? sym_index(a, c) : sym_index(c, a)];
+      if (!initialize) {
+        const int pa = pv_index(a), pc = pv_index(c);
+        if (pa >= 0 && pc >= 0) {
+          if (has_next) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) s += Dr[k * 6 + pa] * (dv[k] * dv[k]) * Dr[k * 6 + pc];
+            val += Sigma * s;
+          }
+          if (has_prev && pa == pc) val += Sigma * dv[pa] * dv[pa];
+        } else if (pa < 0 && pc < 0) {
+          val += Sigma * Dr[46 + (a - 3) * 3 + (c - 3)];
+        }
+      }
+    } else if (e < 162) {
+      const int a = (e - 81) / 9, c = (e - 81) % 9;
+      if (!initialize && has_next) {
+        const int pa = pv_index(a), pc = pv_index(c);
+        if (pa >= 0 && pc >= 0) val = -Sigma * Dr[pc * 6 + pa] * (dv[pc] * dv[pc]);
+        else if (pa < 0 && pc < 0) val = Sigma * Dr[55 + (a - 3) * 3 + (c - 3)];
+      }
+    } else {
+      const int a = e - 162;
+      if (a < 6) val = invw * G[21 + a];
+      if (!initialize) {
+        const int pa = pv_index(a);
+        if (pa >= 0) {
+          if (has_next) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) s += Dr[k * 6 + pa] * dv[k] * Dr[36 + k];
+            val -= Sigma * s;
+          }
+          if (has_prev) val += Sigma * dv[pa] * rp[pa];
+        } else {
+          val -= Sigma * Dr[43 + (a - 3)];
+        }
+      }
+    }
+    out[e] = val;
+  }
+  if (lane == 0) out[171] = 0.0;
+}
+
+int launch_system_build(vinsat_batch* b, int initialize, double Sigma, double vel_coeff) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->T == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_SYSTEM, k_system, ceil_div(b->T, 8), 256, 0, b->T, b->gap, b->fprob, b->wmax, b->grec, b->drec,
+            initialize, Sigma, vel_coeff, b->srec);
+  return VINSAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-problem reductions: one warp per problem, lane-strided over the problem's frames, shuffle tree
+// (fixed order => deterministic accept decisions)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// init_residual = mean |[r_obs ; sqrt(Sigma) r_pred]| (BA_filtering.py:51); also arms the LM loop.
+__global__ void __launch_bounds__(128) k_init_residual(int P, const int64_t* __restrict__ frame_off,
+                                                       const int64_t* __restrict__ obs_off,
+                                                       const int32_t* __restrict__ gap,
+                                                       const double* __restrict__ grec,
+                                                       const double* __restrict__ drec, int initialize,
+                                                       double sqrt_sigma, const double* __restrict__ lam_in,
+                                                       double* __restrict__ lam, double* __restrict__ init_res,
+                                                       int32_t* __restrict__ active, int32_t* __restrict__ ntrials) {
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= P) return;
+  const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
+  double so = 0.0, sd = 0.0;
+  for (int64_t f = f0 + lane; f < f1; f += 32) {
+    so += grec[f * VS_GREC + 27];
+    if (!initialize && gap[f] > 0) {
+      const double* d = drec + f * VS_DREC + 36;
+      sd += fabs(d[0]) + fabs(d[1]) + fabs(d[2]) + fabs(d[3]) + fabs(d[4]) + fabs(d[5]) + fabs(d[6]);
+    }
+  }
+  so = warp_sum(so);
+  sd = warp_sum(sd);
+  if (lane == 0) {
+    const double n = 2.0 * (double)(obs_off[p + 1] - obs_off[p]) + (initialize ? 6.0 : 7.0) * (double)max((long long)(f1 - f0 - 1), 0ll);
+    init_res[p] = (so + sqrt_sigma * sd) / n;
+    lam[p] = lam_in[p];
+    active[p] = (f1 > f0) ? 1 : 0;
+    ntrials[p] = 0;
+  }
+}
+
+int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double, const double* d_lam_in) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->P == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_ACCEPT, k_init_residual, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off,
+            b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
+            b->active, b->ntrials);
+  return VINSAT_OK;
+}
+
+// accept test (BA_filtering.py:66-79)
+__global__ void __launch_bounds__(128) k_accept(int P, const int64_t* __restrict__ frame_off,
+                                                const int64_t* __restrict__ obs_off,
+                                                const unsigned long long* __restrict__ wmax,
+                                                const double* __restrict__ e_obs, const double* __restrict__ e_dyn,
+                                                int initialize, double sqrt_sigma,
+                                                const double* __restrict__ init_res, double* __restrict__ lam,
+                                                double* __restrict__ lam_next, int32_t* __restrict__ active,
+                                                int32_t* __restrict__ ntrials, int32_t* __restrict__ flags) {
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (p >= P) return;
+  if (!active[p]) return;
+  const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
+  double so = 0.0, sd = 0.0;
+  for (int64_t f = f0 + lane; f < f1; f += 32) {
+    so += e_obs[f];
+    if (!initialize && f + 1 < f1) sd += e_dyn[f];
+  }
+  so = warp_sum(so);
+  sd = warp_sum(sd);
+  if (lane == 0) {
+    const unsigned long long wb = wmax[p];
+    const double invw = wb ? 1.0 / __longlong_as_double((long long)wb) : 0.0;
+    const double n = 2.0 * (double)(obs_off[p + 1] - obs_off[p]) + (initialize ? 6.0 : 7.0) * (double)max((long long)(f1 - f0 - 1), 0ll);
+    const double residual = (invw * so + sqrt_sigma * sd) / n;
+    const double l = lam[p] * 10.0;                       // :72
+    lam[p] = l;
+    ntrials[p] += 1;
+    const bool done = (residual < init_res[p]) || (l > 1e4);   // :73-77
+    if (done) {
+      active[p] = 0;
+      lam_next[p] = fmax(fmin(1e-1, l * 0.01), 1e-4);     // :79
+    } else {
+      atomicAdd(&flags[0], 1);
+    }
+  }
+}
+
+int launch_accept(vinsat_batch* b, int initialize, double Sigma) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->P == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_ACCEPT, k_accept, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
+            b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
+            b->ntrials, b->flags);
+  return VINSAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batched block-tridiagonal LU solve + retraction (BA_filtering.py:54-60).  One warp per problem.
+//
+// Forward sweep, frame i: the augmented 9x19 block [S_i | U_i | b~_i] is held one COLUMN per lane
+// (lanes 0..18, 9 registers each); Gauss-Jordan without pivoting (the symmetric part of S_i is positive
+// definite) broadcasts the pivot column through shared memory.  Afterwards lanes 9..17 hold
+// W_i = S_i^-1 U_i and lane 18 holds y_i = S_i^-1 b~_i; S_{i+1} = D_{i+1} + lam I - U_i^T W_i and
+// b~_{i+1} = b_{i+1} - U_i^T y_i.  Backward sweep: delta_i = y_i - W_i delta_{i+1}, fused with the
+// retraction p+dp, normalize(q (x) exp(dtheta)), v+dv.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSolveWarps = 4;
+
+__global__ void __launch_bounds__(kSolveWarps * 32) k_solve_retract(int P, const int64_t* __restrict__ frame_off,
+                                                                   const int32_t* __restrict__ active,
+                                                                   const double* __restrict__ lam,
+                                                                   const double* __restrict__ srec,
+                                                                   double* __restrict__ wrec,
+                                                                   double* __restrict__ delta,
+                                                                   const double* __restrict__ st,
+                                                                   double* __restrict__ st_new,
+                                                                   double* __restrict__ lam32_last) {
+  __shared__ double s_col[kSolveWarps][2][9];
+  __shared__ double s_U[kSolveWarps][81];
+  __shared__ double s_W[kSolveWarps][90];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p = blockIdx.x * kSolveWarps + warp;
+  if (p >= P) return;
+  if (!active[p]) return;
+  const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
+  if (f1 <= f0) return;
+  const double lam32 = (double)(float)lam[p];       // torch.eye(n)*lamda is float32
+  if (lane == 0) lam32_last[p] = lam32;
+  const int c = lane;
+  // offset of element (r, c) inside a system record
+  const int base = c < 9 ? c : (c < 18 ? 81 + (c - 9) : 162);
+  const int rstride = c < 18 ? 9 : 1;
+  double a[9], nxt[9], corr[9];
+#pragma unroll
+  for (int r = 0; r < 9; r++) { corr[r] = 0.0; nxt[r] = 0.0; }
+  if (c < 19) {
+    const double* rec = srec + f0 * VS_SREC;
+#pragma unroll
+    for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
+  }
+  double (*colk)[9] = s_col[warp];
+  double* Us = s_U[warp];
+  double* Ws = s_W[warp];
+  for (int64_t f = f0; f < f1; f++) {
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      double v = nxt[r];
+      if (c < 9) v += (r == c ? lam32 : 0.0) - corr[r];
+      else if (c == 18) v -= corr[r];
+      a[r] = v;
+    }
+    if (f + 1 < f1 && c < 19) {
+      const double* rec = srec + (f + 1) * VS_SREC;
+#pragma unroll
+      for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
+    }
+    if (c >= 9 && c < 18) {
+#pragma unroll
+      for (int r = 0; r < 9; r++) Us[r * 9 + (c - 9)] = a[r];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      if (c == k) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) colk[k & 1][r] = a[r];
+      }
+      __syncwarp();
+      double pk[9];
+#pragma unroll
+      for (int r = 0; r < 9; r++) pk[r] = colk[k & 1][r];
+      const double inv = 1.0 / pk[k];
+      const double pr = a[k] * inv;
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        if (r == k) a[r] = pr;
+        else a[r] = fma(-pk[r], pr, a[r]);
+      }
+    }
+    if (c >= 9 && c < 19) {
+      double* w = wrec + f * VS_WREC + (c - 9) * 9;
+#pragma unroll
+      for (int r = 0; r < 9; r++) { w[r] = a[r]; Ws[(c - 9) * 9 + r] = a[r]; }
+    }
+    __syncwarp();
+    if (f + 1 < f1 && (c < 9 || c == 18)) {
+      const double* wc = Ws + (c < 9 ? c : 9) * 9;
+      double wv[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) wv[k] = wc[k];
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) s = fma(Us[k * 9 + r], wv[k], s);
+        corr[r] = s;
+      }
+    }
+    __syncwarp();
+  }
+  // backward sweep + retraction
+  double dn[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) dn[k] = 0.0;
+  for (int64_t f = f1 - 1; f >= f0; f--) {
+    double dr = 0.0;
+    if (lane < 9) {
+      const double* w = wrec + f * VS_WREC;
+      dr = w[81 + lane];
+      if (f + 1 < f1) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) dr = fma(-w[k * 9 + lane], dn[k], dr);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) dn[k] = __shfl_sync(0xffffffffu, dr, k);
+    const double* s = st + f * 10;
+    double* sn = st_new + f * 10;
+    if (lane < 9) delta[f * 9 + lane] = dr;
+    if (lane < 3) sn[lane] = s[lane] + dr;
+    else if (lane >= 6 && lane < 9) sn[lane + 1] = s[lane + 1] + dr;
+    else if (lane == 3) {
+      const Quat q = {s[3], s[4], s[5], s[6]};
+      Quat e = qexp(dn[3], dn[4], dn[5]);
+      Quat n = qmul(q, e);
+      const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z + n.w * n.w);
+      sn[3] = n.x / nn; sn[4] = n.y / nn; sn[5] = n.z / nn; sn[6] = n.w / nn;
+    }
+  }
+}
+
+int launch_solve_retract(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->P == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_SOLVE, k_solve_retract, ceil_div(b->P, kSolveWarps), kSolveWarps * 32, 0, (int)b->P,
+            b->d_frame_off, b->active, b->lam, b->srec, b->wrec, b->delta, b->st, b->st_new, b->lam32_last);
+  return VINSAT_OK;
+}
+
+}  // namespace vs

@@ -1,0 +1,49 @@
+// Kernel launchers (device pointers; all run on ctx->stream).  Internal.
+#pragma once
+#include "batch.h"
+
+namespace vs {
+
+// ---- kernels_obs.cu ---------------------------------------------------------------------------------
+// Stand-alone a1 on reference-layout (AoS) device buffers.
+int launch_project_aos(vinsat_ctx* ctx, int64_t T, int64_t M, const double* states, const double* intr,
+                       const double* xyz, const int64_t* ii, double* uv_out, double* Jg_out, int32_t* err_flag);
+// Headline: residual + Jacobian for resident SoA observations -> r[2][M], J[12][M].
+int launch_resjac(vinsat_batch* b);
+// r = uv - project(st) for every observation (input of the robust scale).
+int launch_obs_residual(vinsat_batch* b);
+// Fused projection + Jacobian + robust weight + per-frame JtWJ / JtWr (+ sum|r|, max w).
+int launch_obs_assemble(vinsat_batch* b, double alpha);
+// Trial: per-frame sum of wu*|uv - project(st_new)|.
+int launch_obs_trial(vinsat_batch* b);
+// Observation indexing on the device: oframe, obs_start (CSR), sortedness check.
+int launch_obs_index(vinsat_batch* b, const int64_t* d_ii_local);
+// AoS [n][ncol] <-> SoA [ncol][n] through shared memory.
+int launch_aos_to_soa(vinsat_ctx* ctx, const double* aos, double* soa, int64_t n, int ncol);
+int launch_soa_to_aos(vinsat_ctx* ctx, const double* soa, double* aos, int64_t n, int ncol);
+
+// ---- kernels_dyn.cu ---------------------------------------------------------------------------------
+// RK4 + STM for the pairs listed in `order` (2 threads per pair): writes Phi, r6 into drec; x_pred optional.
+int launch_dynamics_stm(vinsat_ctx* ctx, int64_t n_pairs, const int32_t* order, const double* st,
+                        const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred);
+// Quaternion smoothness terms per frame: rho, qgrad, Hq_diag, Hq_off into drec.
+int launch_quat_terms(vinsat_ctx* ctx, int64_t T, const double* st, const double* crot, const int32_t* gap,
+                      double quat_coeff, double* drec);
+// Trial: residual-only propagation; e_dyn[f] = sum |r_pred(f)| over the 7 components (0 where no pair).
+int launch_dyn_trial(vinsat_ctx* ctx, int64_t n_pairs, const int32_t* order, const double* st,
+                     const double* crot, const int32_t* gap, const int32_t* active, const int32_t* fprob,
+                     double quat_coeff, double vel_coeff, int mode, double* e_dyn, double* r7_out);
+int launch_chain(vinsat_ctx* ctx, int64_t n_steps, double dt, const double* state0, const double* vel0,
+                 const double* omega, double* states_out);
+int launch_orbit_propagate(vinsat_ctx* ctx, int64_t n_traj, int64_t n_steps, int64_t stride, double h,
+                           const double* x0, double* out);
+
+// ---- kernels_solve.cu -------------------------------------------------------------------------------
+int launch_select_median(vinsat_batch* b);                       // c_obs[p] = lower median of |r|
+int launch_system_build(vinsat_batch* b, int initialize, double Sigma, double vel_coeff);
+int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double lamda_host_default,
+                         const double* d_lam_in);
+int launch_solve_retract(vinsat_batch* b);
+int launch_accept(vinsat_batch* b, int initialize, double Sigma);
+
+}  // namespace vs
