@@ -236,10 +236,14 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
     VS_TRY(launch_dynamics_stm(ctx, b->n_pairs, b->dyn_order, b->st, b->gap, vel_coeff, mode, b->drec, nullptr));
     VS_TRY(launch_quat_terms(ctx, b->T, b->st, b->crot, b->gap, quat_coeff, b->drec));
   }
-  VS_TRY(launch_system_build(b, initialize, Sigma, vel_coeff));
+  // initialize phase: block-diagonal system, solved straight from the observation records (k_solve_init);
+  // the full records are only materialised on demand (last_hessian / debug_fetch).
+  if (!initialize) VS_TRY(launch_system_build(b, 0, Sigma, vel_coeff));
+  b->srec_valid = !initialize;
+  b->last_sigma = Sigma;
   VS_TRY(launch_init_residual(b, initialize, Sigma, 0.0, lam_dev_in));
   for (int trial = 0; trial < 16; trial++) {
-    VS_TRY(launch_solve_retract(b));
+    VS_TRY(launch_solve_retract(b, initialize));
     VS_TRY(launch_obs_trial(b));
     if (!initialize)
       VS_TRY(launch_dyn_trial(ctx, b->n_pairs, b->dyn_order, b->st_new, b->crot, b->gap, b->active, b->fprob,
@@ -285,11 +289,19 @@ int vinsat_batch_od_solve(vinsat_batch* b, int num_iters, int n_init, double lam
   return VINSAT_OK;
 }
 
+static int ensure_srec(vinsat_batch* b) {
+  if (b->srec_valid) return VINSAT_OK;
+  VS_TRY(launch_system_build(b, b->last_initialize, b->last_sigma, 100.0));
+  b->srec_valid = true;
+  return VINSAT_OK;
+}
+
 int vinsat_batch_last_hessian(vinsat_batch* b, double* out) {
   if (!b || !out) return set_error(b ? b->ctx : nullptr, VINSAT_EINVAL, "vinsat_batch_last_hessian: NULL argument");
   vinsat_ctx* ctx = b->ctx;
   if (!b->have_iter) return set_error(ctx, VINSAT_EINVAL, "no BA iteration has run on this batch");
   VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  VS_TRY(ensure_srec(b));
   std::vector<double> l32(b->P);
   VS_CUDA(ctx, cudaMemcpyAsync(l32.data(), b->lam32_last, b->P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   for (int64_t p = 0; p < b->P; p++) {
@@ -310,6 +322,7 @@ int vinsat_batch_debug_fetch(vinsat_batch* b, double* r_obs, double* weights, do
   vinsat_ctx* ctx = b->ctx;
   if (!b->have_iter) return set_error(ctx, VINSAT_EINVAL, "no BA iteration has run on this batch");
   VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  VS_TRY(ensure_srec(b));
   VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   const int64_t P = b->P, T = b->T, M = b->M;
   if (r_obs && M) {

@@ -56,5 +56,7 @@ struct vinsat_batch {
   int32_t* flags = nullptr;    // [4]: 0 = n_active, 1 = index error
   int32_t* h_flags = nullptr;  // pinned mirror
   bool have_iter = false;
+  bool srec_valid = false;
+  double last_sigma = 0.0;
   int last_initialize = 0;
 };

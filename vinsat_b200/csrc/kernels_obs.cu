@@ -218,20 +218,26 @@ int launch_obs_residual(vinsat_batch* b) {
 // A group of 8 lanes owns one frame and strides over its observations; the 28 partial sums are combined
 // with xor-shuffles (fixed tree => deterministic) and written as one 224 B record.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kGroup = 8;
-
+template <int G>
 __device__ __forceinline__ double group_sum(double v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  if (G >= 8) v += __shfl_xor_sync(0xffffffffu, v, 4);
+  if (G >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
   v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ double group_max(double v) {
+  if (G >= 8) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  if (G >= 4) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return v;
 }
 
 struct WeightParams {
-  double inv_am2;   // 1/|alpha-2| is NOT used: the reference divides, so keep |alpha-2| itself
-  double am2;       // |alpha - 2|
+  double am2;       // |alpha - 2| (the reference divides by it)
   double ex;        // alpha/2 - 1
   int alpha_is_two;
+  int ex_is_mhalf;  // alpha == 1 (every iteration >= 3): pow(x, -0.5) == 1/sqrt(x)
 };
 
 // BA_filtering.py:24, one component: ((r/c)^2/|alpha-2| + 1)^(alpha/2-1) / c^2
@@ -239,10 +245,13 @@ __device__ __forceinline__ double robust_component(double r, double c, const Wei
   const double c2 = c * c;
   if (wp.alpha_is_two) return 1.0 / c2;     // pow(inf|nan, 0) == 1 (IEEE / torch), SURVEY section 7
   const double q = r / c;
-  return pow(q * q / wp.am2 + 1.0, wp.ex) / c2;
+  const double base = q * q / wp.am2 + 1.0;
+  if (wp.ex_is_mhalf) return (1.0 / sqrt(base)) / c2;
+  return pow(base, wp.ex) / c2;
 }
 
-__global__ void __launch_bounds__(256) k_obs_assemble(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
+template <int kGroup>
+__global__ void __launch_bounds__(128, 3) k_obs_assemble(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
                                                       const int32_t* __restrict__ fprob,
                                                       const double* __restrict__ X, const double* __restrict__ uv,
                                                       const double* __restrict__ conf, const double* __restrict__ st,
@@ -289,10 +298,8 @@ __global__ void __launch_bounds__(256) k_obs_assemble(int64_t T, int64_t M, cons
     }
   }
 #pragma unroll
-  for (int i = 0; i < VS_GREC; i++) acc[i] = group_sum(acc[i]);
-  wloc = fmax(wloc, __shfl_xor_sync(0xffffffffu, wloc, 4));
-  wloc = fmax(wloc, __shfl_xor_sync(0xffffffffu, wloc, 2));
-  wloc = fmax(wloc, __shfl_xor_sync(0xffffffffu, wloc, 1));
+  for (int i = 0; i < VS_GREC; i++) acc[i] = group_sum<kGroup>(acc[i]);
+  wloc = group_max<kGroup>(wloc);
   if (valid) {
     double* g = grec + f * VS_GREC;
 #pragma unroll
@@ -306,17 +313,24 @@ int launch_obs_assemble(vinsat_batch* b, double alpha) {
   vinsat_ctx* ctx = b->ctx;
   WeightParams wp;
   wp.am2 = fabs(alpha - 2.0);
-  wp.inv_am2 = 0.0;
   wp.ex = alpha / 2.0 - 1.0;
   wp.alpha_is_two = (wp.ex == 0.0) ? 1 : 0;
+  wp.ex_is_mhalf = (wp.ex == -0.5) ? 1 : 0;
   VS_CUDA(ctx, cudaMemsetAsync(b->wmax, 0, b->P * sizeof(unsigned long long), ctx->stream));
   if (b->T == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble, ceil_div(b->T * kGroup, 256), 256, 0, b->T, b->M, b->obs_start,
-            b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
+  // 4 lanes per frame for sparse frames (<= 16 observations on average), 8 otherwise
+  if (b->M <= 16 * b->T) {
+    VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble<4>, ceil_div(b->T * 4, 128), 128, 0, b->T, b->M, b->obs_start,
+              b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
+  } else {
+    VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble<8>, ceil_div(b->T * 8, 128), 128, 0, b->T, b->M, b->obs_start,
+              b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
+  }
   return VINSAT_OK;
 }
 
 // trial residual, observation part: e_obs[f] = sum_k wu_k (|ru| + |rv|) at st_new (BA_filtering.py:61,66)
+template <int kGroup>
 __global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
                                                    const int32_t* __restrict__ fprob,
                                                    const int32_t* __restrict__ active, const double* __restrict__ X,
@@ -342,15 +356,20 @@ __global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const i
       }
     }
   }
-  e = group_sum(e);
+  e = group_sum<kGroup>(e);
   if (valid && live && gl == 0) e_obs[f] = e;
 }
 
 int launch_obs_trial(vinsat_batch* b) {
   vinsat_ctx* ctx = b->ctx;
   if (b->T == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_TRIAL, k_obs_trial, ceil_div(b->T * kGroup, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
-            b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs);
+  if (b->M <= 16 * b->T) {
+    VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<4>, ceil_div(b->T * 4, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
+              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs);
+  } else {
+    VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<8>, ceil_div(b->T * 8, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
+              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs);
+  }
   return VINSAT_OK;
 }
 

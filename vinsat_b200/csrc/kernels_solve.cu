@@ -300,26 +300,34 @@ int launch_accept(vinsat_batch* b, int initialize, double Sigma) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// batched block-tridiagonal LU solve + retraction (BA_filtering.py:54-60).  One warp per problem.
+// batched block-tridiagonal LU solve (BA_filtering.py:54-55).  One warp per problem.
 //
 // Forward sweep, frame i: the augmented 9x19 block [S_i | U_i | b~_i] is held one COLUMN per lane
 // (lanes 0..18, 9 registers each); Gauss-Jordan without pivoting (the symmetric part of S_i is positive
 // definite) broadcasts the pivot column through shared memory.  Afterwards lanes 9..17 hold
 // W_i = S_i^-1 U_i and lane 18 holds y_i = S_i^-1 b~_i; S_{i+1} = D_{i+1} + lam I - U_i^T W_i and
-// b~_{i+1} = b_{i+1} - U_i^T y_i.  Backward sweep: delta_i = y_i - W_i delta_{i+1}, fused with the
-// retraction p+dp, normalize(q (x) exp(dtheta)), v+dv.
+// b~_{i+1} = b_{i+1} - U_i^T y_i.  Backward sweep: delta_i = y_i - W_i delta_{i+1}.
+// The sweep is a latency chain (T dependent 9x9 eliminations), so global loads are software-prefetched one
+// frame ahead and the pivot reciprocal uses rcp.approx + two Newton steps instead of an IEEE division.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSolveWarps = 4;
+constexpr int kSolveWarps = 1;
 
-__global__ void __launch_bounds__(kSolveWarps * 32) k_solve_retract(int P, const int64_t* __restrict__ frame_off,
-                                                                   const int32_t* __restrict__ active,
-                                                                   const double* __restrict__ lam,
-                                                                   const double* __restrict__ srec,
-                                                                   double* __restrict__ wrec,
-                                                                   double* __restrict__ delta,
-                                                                   const double* __restrict__ st,
-                                                                   double* __restrict__ st_new,
-                                                                   double* __restrict__ lam32_last) {
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+__global__ void __launch_bounds__(kSolveWarps * 32) k_solve(int P, const int64_t* __restrict__ frame_off,
+                                                           const int32_t* __restrict__ active,
+                                                           const double* __restrict__ lam,
+                                                           const double* __restrict__ srec,
+                                                           double* __restrict__ wrec, double* __restrict__ delta,
+                                                           double* __restrict__ lam32_last) {
   __shared__ double s_col[kSolveWarps][2][9];
   __shared__ double s_U[kSolveWarps][81];
   __shared__ double s_W[kSolveWarps][90];
@@ -373,8 +381,7 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_solve_retract(int P, const
       double pk[9];
 #pragma unroll
       for (int r = 0; r < 9; r++) pk[r] = colk[k & 1][r];
-      const double inv = 1.0 / pk[k];
-      const double pr = a[k] * inv;
+      const double pr = a[k] * fast_rcp(pk[k]);
 #pragma unroll
       for (int r = 0; r < 9; r++) {
         if (r == k) a[r] = pr;
@@ -402,42 +409,135 @@ __global__ void __launch_bounds__(kSolveWarps * 32) k_solve_retract(int P, const
     }
     __syncwarp();
   }
-  // backward sweep + retraction
-  double dn[9];
+  // backward sweep: lane r < 9 owns row r; the next record is prefetched while the current one is used
+  double dn[9], wcur[10], wnx[10];
 #pragma unroll
   for (int k = 0; k < 9; k++) dn[k] = 0.0;
-  for (int64_t f = f1 - 1; f >= f0; f--) {
-    double dr = 0.0;
-    if (lane < 9) {
-      const double* w = wrec + f * VS_WREC;
-      dr = w[81 + lane];
-      if (f + 1 < f1) {
 #pragma unroll
-        for (int k = 0; k < 9; k++) dr = fma(-w[k * 9 + lane], dn[k], dr);
-      }
+  for (int k = 0; k < 10; k++) { wcur[k] = 0.0; wnx[k] = 0.0; }
+  const int lr = lane < 9 ? lane : 0;
+  {
+    const double* w = wrec + (f1 - 1) * VS_WREC;
+#pragma unroll
+    for (int k = 0; k < 9; k++) wnx[k] = w[k * 9 + lr];
+    wnx[9] = w[81 + lr];
+  }
+  for (int64_t f = f1 - 1; f >= f0; f--) {
+#pragma unroll
+    for (int k = 0; k < 10; k++) wcur[k] = wnx[k];
+    if (f > f0) {
+      const double* w = wrec + (f - 1) * VS_WREC;
+#pragma unroll
+      for (int k = 0; k < 9; k++) wnx[k] = w[k * 9 + lr];
+      wnx[9] = w[81 + lr];
+    }
+    double dr = wcur[9];
+    if (f + 1 < f1) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) dr = fma(-wcur[k], dn[k], dr);
     }
 #pragma unroll
     for (int k = 0; k < 9; k++) dn[k] = __shfl_sync(0xffffffffu, dr, k);
-    const double* s = st + f * 10;
-    double* sn = st_new + f * 10;
     if (lane < 9) delta[f * 9 + lane] = dr;
-    if (lane < 3) sn[lane] = s[lane] + dr;
-    else if (lane >= 6 && lane < 9) sn[lane + 1] = s[lane + 1] + dr;
-    else if (lane == 3) {
-      const Quat q = {s[3], s[4], s[5], s[6]};
-      Quat e = qexp(dn[3], dn[4], dn[5]);
-      Quat n = qmul(q, e);
-      const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z + n.w * n.w);
-      sn[3] = n.x / nn; sn[4] = n.y / nn; sn[5] = n.z / nn; sn[6] = n.w / nn;
-    }
   }
 }
 
-int launch_solve_retract(vinsat_batch* b) {
+// initialize phase (BA_utils.py:463-466 => no dynamics terms): the system is block diagonal, every frame is
+// an independent SPD 6x6 pose block (+ lam I) and three decoupled velocity rows with zero right-hand side.
+// One thread per frame, Cholesky in registers, straight from the observation record (no srec round trip).
+__global__ void __launch_bounds__(128) k_solve_init(int64_t T, const int32_t* __restrict__ fprob,
+                                                    const int32_t* __restrict__ active,
+                                                    const double* __restrict__ lam,
+                                                    const unsigned long long* __restrict__ wmax,
+                                                    const double* __restrict__ grec, double* __restrict__ delta,
+                                                    double* __restrict__ lam32_last) {
+  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= T) return;
+  const int p = fprob[f];
+  if (!active[p]) return;
+  const double lam32 = (double)(float)lam[p];
+  lam32_last[p] = lam32;     // same value from every frame of the problem
+  const unsigned long long wb = wmax[p];
+  const double invw = wb ? 1.0 / __longlong_as_double((long long)wb) : 0.0;
+  const double* g = grec + f * VS_GREC;
+  double L[6][6], y[6];
+  {
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = a; b < 6; b++) { L[b][a] = invw * g[idx++] + (a == b ? lam32 : 0.0); }
+#pragma unroll
+    for (int a = 0; a < 6; a++) y[a] = invw * g[21 + a];
+  }
+  // in-place Cholesky of the lower triangle
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    double d = L[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d = fma(-L[j][k], L[j][k], d);
+    d = sqrt(d);
+    L[j][j] = d;
+    const double inv = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      double s = L[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) s = fma(-L[i][k], L[j][k], s);
+      L[i][j] = s * inv;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    double s = y[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s = fma(-L[i][k], y[k], s);
+    y[i] = s / L[i][i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    double s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s = fma(-L[k][i], y[k], s);
+    y[i] = s / L[i][i];
+  }
+  double* d = delta + f * 9;
+#pragma unroll
+  for (int i = 0; i < 6; i++) d[i] = y[i];
+  d[6] = 0.0; d[7] = 0.0; d[8] = 0.0;
+}
+
+// retraction (BA_filtering.py:56-60): p + dp, normalize(q (x) exp(dtheta)), v + dv; one thread per frame
+__global__ void __launch_bounds__(128) k_retract(int64_t T, const int32_t* __restrict__ fprob,
+                                                 const int32_t* __restrict__ active,
+                                                 const double* __restrict__ st, const double* __restrict__ delta,
+                                                 double* __restrict__ st_new) {
+  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= T) return;
+  if (!active[fprob[f]]) return;
+  const double* s = st + f * 10;
+  const double* d = delta + f * 9;
+  double* o = st_new + f * 10;
+  o[0] = s[0] + d[0]; o[1] = s[1] + d[1]; o[2] = s[2] + d[2];
+  o[7] = s[7] + d[6]; o[8] = s[8] + d[7]; o[9] = s[9] + d[8];
+  const Quat q = {s[3], s[4], s[5], s[6]};
+  const Quat n = qmul(q, qexp(d[3], d[4], d[5]));
+  const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z + n.w * n.w);
+  o[3] = n.x / nn; o[4] = n.y / nn; o[5] = n.z / nn; o[6] = n.w / nn;
+}
+
+int launch_solve_retract(vinsat_batch* b, int initialize) {
   vinsat_ctx* ctx = b->ctx;
-  if (b->P == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_SOLVE, k_solve_retract, ceil_div(b->P, kSolveWarps), kSolveWarps * 32, 0, (int)b->P,
-            b->d_frame_off, b->active, b->lam, b->srec, b->wrec, b->delta, b->st, b->st_new, b->lam32_last);
+  if (b->P == 0 || b->T == 0) return VINSAT_OK;
+  if (initialize) {
+    VS_LAUNCH(ctx, F_SOLVE, k_solve_init, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->lam, b->wmax,
+              b->grec, b->delta, b->lam32_last);
+  } else {
+    VS_LAUNCH(ctx, F_SOLVE, k_solve, ceil_div(b->P, kSolveWarps), kSolveWarps * 32, 0, (int)b->P, b->d_frame_off,
+              b->active, b->lam, b->srec, b->wrec, b->delta, b->lam32_last);
+  }
+  VS_LAUNCH(ctx, F_RETRACT, k_retract, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->st, b->delta,
+            b->st_new);
   return VINSAT_OK;
 }
 

@@ -43,7 +43,7 @@ int launch_select_median(vinsat_batch* b);                       // c_obs[p] = l
 int launch_system_build(vinsat_batch* b, int initialize, double Sigma, double vel_coeff);
 int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double lamda_host_default,
                          const double* d_lam_in);
-int launch_solve_retract(vinsat_batch* b);
+int launch_solve_retract(vinsat_batch* b, int initialize);
 int launch_accept(vinsat_batch* b, int initialize, double Sigma);
 
 }  // namespace vs
