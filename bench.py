@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Benchmark of the VINSat estimation hot path on B200 (BASELINE.json metric: OD solves/s (batched),
+with the landmark-obs residual+Jacobian evals/s of the headline kernel reported beside it).
+
+    python bench.py --gpus N --steps K --warmup W          # N>1: launched by torch.distributed.run
+    python bench.py --impl reference ...                    # the CPU arm (oracle port, all host cores)
+
+One "step" = one batched OD solve (streaming_version's schedule on one window, od_pipe.py:918,1036-1040:
+20 BA iterations, the first 10 with initialize=True) of BASELINE.json configs[1]: 1024 independent
+synthetic OD problems x 1000 frames x 10 landmark observations per frame on each GPU (weak scaling:
+problems are independent, no data-path collective).  `value` times the step with inputs resident in HBM;
+`e2e` times the same step through the public API with pinned HOST buffers (H2D of every input and D2H of
+the solved states inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "OD solves/s (batched)"
+UNIT = "solves/s"
+# algorithmic work per unit
+BYTES_PER_OBS_RESJAC = 156.0          # X 24 + uv 16 + frame id 4 read; r 16 + J(2x6) 96 written
+BYTES_PER_FRAME_STATE = 88.0          # state row (p,q) 56 + intrinsics 32, amortised over the frame's observations
+BYTES_PER_FRAME_SOLVE = 2880.0        # D,U,b read 1368 + W,y written 720 + W,y read 720 + delta written 72
+BYTES_PER_FRAME_SOLVE_INIT = 288.0    # obs record read 216 + delta written 72
+FLOP_PER_RK4_STM_STEP = 1332.0        # DFMA*2+DMUL+DADD of one single-thread 6-column RK4+STM step (cuobjdump); the
+                                      # shipped 2-thread x 3-column kernel executes 2012 (state stages duplicated)
+
+
+def workload(args):
+    return dict(P=args.problems, T=args.frames, K=args.obs_per_frame, num_iters=20, n_init=10, gap_max=20)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 9] or [r for (_, r) in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (NumPy restatement of the reference algorithm), one problem per process
+# --------------------------------------------------------------------------------------------------
+def _cpu_solve_one(args):
+    seed, T, K = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ba_oracle as o
+    from vinsat_b200 import synth
+    pr = synth.make_problem(seed, T, K)
+    t0 = time.perf_counter()
+    st, _, _ = o.od_solve(pr["states0"].copy(), pr["cum_rot"], pr["uv"], pr["xyz"], pr["ii"], pr["time_idx"],
+                          pr["intr"], pr["conf"])
+    dt = time.perf_counter() - t0
+    return dt, float(np.abs(st[:, :3] - pr["states_gt"][:, :3]).max())
+
+
+def cpu_baseline(T, K, n_problems, procs):
+    """Solves `n_problems` problems of the bench workload with the oracle port on `procs` processes."""
+    import multiprocessing as mp
+    jobs = [(10_000 + i, T, K) for i in range(n_problems)]
+    t0 = time.perf_counter()
+    if procs > 1:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            res = pool.map(_cpu_solve_one, jobs)
+    else:
+        res = [_cpu_solve_one(j) for j in jobs]
+    wall = time.perf_counter() - t0
+    return dict(value=n_problems / wall, unit=UNIT, cores=procs, kind="port",
+                sample="%d OD solves (T=%d frames, %d obs, 20 BA iterations) with oracle/ba_oracle.py (NumPy closed-form "
+                       "Jacobians + banded LU; the reference's own autograd path is ~1e3x slower, BASELINE.md section 2), "
+                       "%d processes; %.1f s wall, %.1f s per solve" % (n_problems, T, T * K, procs, wall,
+                                                                         float(np.mean([r[0] for r in res]))))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    w = workload(args)
+    n = 4 * max(cores, 1) if args.cpu_problems <= 0 else args.cpu_problems
+    vals = []
+    cb = None
+    for _ in range(max(args.warmup, 0)):
+        pass            # CPU arm: nothing to warm (process start-up is outside the timed solve)
+    for _ in range(max(1, min(args.steps, 2))):
+        cb = cpu_baseline(w["T"], w["K"], n, cores)
+        vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "bounded sample of configs[1]: %d OD problems x %d frames x %d obs/frame on the host CPU"
+                                  % (n, w["T"], w["K"]), **w},
+           "cpu_baseline": cb,
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from vinsat_b200 import _lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = _lib.Context(local)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)      # the library launches on this stream; torch CUDA events time it
+    w = workload(args)
+    P, T, K = w["P"], w["T"], w["K"]
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # synthetic problems of this rank (seed = global problem index), pinned host copies for the e2e leg
+    prs = synth.make_batch(P, T, K, seed0=rank * P)
+    arrays = _lib.concat_problems(prs)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in arrays.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in pinned.items() if k not in ("frame_off", "obs_off"))
+    batch = _lib.Batch(ctx, pinned)
+    states0_dev = torch.from_numpy(arrays["states"]).to(dev)
+    out_pinned = torch.empty((batch.T, 10), dtype=torch.float64).pin_memory()
+    d2h_bytes = out_pinned.numel() * 8
+
+    def step_resident():
+        ctx.check(ctx.lib.vinsat_batch_set_states(batch.h, _lib.MEM_DEVICE, _lib._ptr(states0_dev)))
+        batch.od_solve(20, 10, 1e-4)
+
+    def step_e2e():
+        batch.upload(pinned)
+        batch.od_solve(20, 10, 1e-4)
+        batch.get_states(out_pinned)
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        wall = time.perf_counter() - t0
+        return max_over_ranks(e0.elapsed_time(e1) * 1e-3), max_over_ranks(wall)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ctx.enable_timing(True); ctx.reset_timing()
+    l0 = ctx.launch_count()
+    tw0 = time.time()
+    dev_s, wall_s = timed(step_resident, args.steps)
+    tw1 = time.time()
+    launches = ctx.launch_count() - l0
+    fam = ctx.timing()
+    ctx.enable_timing(False)
+    clocks = sampler.stop(tw0, tw1) if sampler else None
+    total_launches = int(sum_over_ranks(launches))
+    value = world * P * args.steps / dev_s
+
+    # sanity: the timed solve converged (states vs simulated truth), so no work was skipped
+    st = batch.get_states()
+    err = max(float(np.abs(st[arrays["frame_off"][p]:arrays["frame_off"][p + 1], :3] - prs[p]["states_gt"][:, :3]).max())
+              for p in range(0, P, max(1, P // 64)))
+
+    # e2e through the public API with host buffers
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    e2e_dev_s, e2e_wall_s = timed(step_e2e, args.steps)
+    e2e_value = world * P * args.steps / e2e_wall_s
+
+    # headline kernel alone: residual + Jacobian for every resident observation (inputs >> L2)
+    for _ in range(3):
+        batch.eval_resjac()
+    ctx.enable_timing(True); ctx.reset_timing()
+    rj_dev_s, _ = timed(batch.eval_resjac, 20)
+    rj = ctx.timing()["project_resjac"]
+    ctx.enable_timing(False)
+    rj_ms = rj[0] / max(rj[1], 1)
+    evals = world * batch.M / (rj_dev_s / 20)
+
+    fp64_peak = ctx.fp64_peak_tflops()
+    hbm_peak, peak_src = peaks()
+
+    if rank == 0:
+        n_frames = batch.T
+        n_pairs = n_frames - P
+        fam_ms = {k: round(v[0] / args.steps, 4) for k, v in fam.items() if v[1]}
+        tot_ms = sum(fam_ms.values())
+        # dominant kernel of the step
+        dom = max(fam_ms, key=fam_ms.get)
+        per_launch = {k: v[0] / v[1] for k, v in fam.items() if v[1]}
+        kern = {}
+        kern["blocktridiag_solve"] = dict(bound="hbm", unit="GB/s", peak=hbm_peak,
+                                          achieved=BYTES_PER_FRAME_SOLVE * n_frames / (per_launch.get("blocktridiag_solve", float("nan")) * 1e-3) / 1e9)
+        if "solve_init" in per_launch:
+            kern["solve_init"] = dict(bound="hbm", unit="GB/s", peak=hbm_peak,
+                                      achieved=BYTES_PER_FRAME_SOLVE_INIT * n_frames / (per_launch["solve_init"] * 1e-3) / 1e9)
+        sum_gap = float(sum(int(pr["time_idx"][-1] - pr["time_idx"][0]) for pr in prs))
+        kern["dynamics_stm"] = dict(bound="fp64", unit="TFLOP/s", peak=fp64_peak,
+                                    achieved=FLOP_PER_RK4_STM_STEP * sum_gap / (per_launch.get("dynamics_stm", float("nan")) * 1e-3) / 1e12)
+        kern["obs_assemble"] = dict(bound="hbm", unit="GB/s", peak=hbm_peak,
+                                    achieved=(60.0 * batch.M + (BYTES_PER_FRAME_STATE + 224.0) * n_frames) / (per_launch.get("obs_assemble", float("nan")) * 1e-3) / 1e9)
+        for k in kern:
+            kern[k]["frac"] = kern[k]["achieved"] / kern[k]["peak"]
+            kern[k]["ms_per_launch"] = per_launch.get(k)
+        rj_bytes = BYTES_PER_OBS_RESJAC * batch.M + BYTES_PER_FRAME_STATE * n_frames
+        rj_roof = dict(bound="hbm", achieved=rj_bytes / (rj_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s", traffic=None,
+                       ms_per_launch=rj_ms, bytes_per_launch=rj_bytes)
+        rj_roof["frac"] = rj_roof["achieved"] / hbm_peak
+        dk = kern.get(dom, kern["blocktridiag_solve"])
+        roofline = dict(kernel=dom if dom in kern else "blocktridiag_solve", bound=dk["bound"],
+                        achieved=dk["achieved"], peak=dk["peak"], unit=dk["unit"], frac=dk["frac"], traffic=None,
+                        peak_source=peak_src, share_of_step=fam_ms.get(dom, 0) / tot_ms)
+        cb = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            cb = cpu_baseline(T, K, 4 * cores if args.cpu_problems <= 0 else args.cpu_problems, cores)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: batch_runner-style Monte Carlo, %d independent OD problems x %d frames x %d "
+                                   "landmark obs/frame per GPU; one step = 20 BA iterations (10 initialize + 10 full) per problem" % (P, T, K),
+                       **w, "problems_total": world * P, "l2_policy": "inputs larger than L2 (per-step working set %.1f GB per GPU)"
+                       % ((batch.T * 3200 + batch.M * 100) / 1e9), "propagator": "step1s (reference CPU `predict`)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": 1e3 * e2e_wall_s / args.steps, "timing": "wall clock, barrier+synchronize both sides, max over ranks"},
+            "gpu_launches": total_launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cb,
+            "extra": {
+                "wall_ms_per_step": 1e3 * wall_s / args.steps,
+                "resjac_evals_per_s": evals, "resjac_roofline": rj_roof,
+                "kernel_ms_per_step": fam_ms, "kernels": kern, "fp64_peak_tflops_measured": fp64_peak,
+                "max_pos_err_vs_truth_km": err,
+            },
+        }
+        print(json.dumps(out))
+    batch.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--problems", type=int, default=1024, help="OD problems per GPU")
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--obs-per-frame", type=int, default=10)
+    ap.add_argument("--cpu-problems", type=int, default=0, help="size of the CPU sample (0 = one per core)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,8 +52,11 @@ int vinsat_abi_version(void);
 int vinsat_device_count(void);
 int vinsat_ctx_create(int device, vinsat_ctx** out);
 int vinsat_ctx_destroy(vinsat_ctx* ctx);
-/* Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = library stream. */
+/* Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream).  NULL is the CUDA legacy
+ * default stream, exactly as for a kernel launch.  vinsat_ctx_reset_stream returns to the library's own
+ * (non-blocking) stream. */
 int vinsat_ctx_set_stream(vinsat_ctx* ctx, void* cuda_stream);
+int vinsat_ctx_reset_stream(vinsat_ctx* ctx);
 int vinsat_ctx_synchronize(vinsat_ctx* ctx);
 const char* vinsat_last_error(const vinsat_ctx* ctx); /* ctx may be NULL: last global error */
 

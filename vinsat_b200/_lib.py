@@ -38,6 +38,7 @@ SIGNATURES = {
     "vinsat_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "vinsat_ctx_destroy": (C.c_int, [C.c_void_p]),
     "vinsat_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vinsat_ctx_reset_stream": (C.c_int, [C.c_void_p]),
     "vinsat_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "vinsat_last_error": (C.c_char_p, [C.c_void_p]),
     "vinsat_landmark_project": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
@@ -147,7 +148,11 @@ class Context:
         self.check(self.lib.vinsat_ctx_synchronize(self.h))
 
     def set_stream(self, cuda_stream):
-        self.check(self.lib.vinsat_ctx_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """cuda_stream: integer handle (torch.cuda.Stream.cuda_stream); 0 = the legacy default stream."""
+        self.check(self.lib.vinsat_ctx_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def reset_stream(self):
+        self.check(self.lib.vinsat_ctx_reset_stream(self.h))
 
     def launch_count(self):
         return int(self.lib.vinsat_ctx_launch_count(self.h))

@@ -9,8 +9,8 @@
 namespace vs {
 
 const char* const kFamilyNames[F_COUNT] = {
-    "project_resjac", "obs_residual", "select_median", "obs_assemble", "dynamics_stm", "system_build",
-    "blocktridiag_solve", "retract", "trial_residual", "accept_reduce", "layout", "orbit_sim", "satcam", "peak"};
+    "project_resjac", "obs_residual", "select_median", "obs_assemble", "dynamics_stm", "quat_terms", "system_build",
+    "blocktridiag_solve", "solve_init", "retract", "trial_residual", "accept_reduce", "layout", "orbit_sim", "satcam", "peak"};
 
 static std::mutex g_err_mu;
 static std::string g_err;
@@ -192,7 +192,15 @@ int vinsat_ctx_set_stream(vinsat_ctx* ctx, void* cuda_stream) {
   if (!ctx) return VINSAT_EINVAL;
   cudaStreamSynchronize(ctx->stream);
   timing_resolve(ctx);
-  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return VINSAT_OK;
+}
+
+int vinsat_ctx_reset_stream(vinsat_ctx* ctx) {
+  if (!ctx) return VINSAT_EINVAL;
+  cudaStreamSynchronize(ctx->stream);
+  timing_resolve(ctx);
+  ctx->stream = ctx->own_stream;
   return VINSAT_OK;
 }
 

@@ -16,9 +16,11 @@ enum Family {
   F_OBS_RESID,        // residuals for the robust scale
   F_SELECT,           // radix select (median) + weights max
   F_OBS_ASSEMBLE,     // fused projection + weights + per-frame JtWJ / JtWr
-  F_DYNAMICS,         // RK4 + STM + quaternion terms
+  F_DYNAMICS,         // RK4 + STM
+  F_QUAT,             // quaternion smoothness gradient / Hessian blocks
   F_SYSTEM,           // block-tridiagonal system build
   F_SOLVE,            // block-tridiagonal LU solve
+  F_SOLVE_INIT,       // initialize phase: per-frame Cholesky
   F_RETRACT,          // retraction
   F_TRIAL,            // trial residual evaluation (obs + dynamics)
   F_ACCEPT,           // per-problem reductions, LM accept test
@@ -97,10 +99,5 @@ struct DevBuf {
   ~DevBuf() { if (p) cudaFree(p); }
   cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)); }
 };
-
-// ---- launchers implemented in the .cu files (device pointers, run on ctx->stream) ----------------
-// layout.cu
-int launch_aos_to_soa(vinsat_ctx* ctx, const double* aos, double* soa, int64_t n, int ncol, int64_t soa_stride);
-int launch_soa_to_aos(vinsat_ctx* ctx, const double* soa, double* aos, int64_t n, int ncol, int64_t soa_stride);
 
 }  // namespace vs

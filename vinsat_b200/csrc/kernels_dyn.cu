@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) k_quat_terms(int64_t T, const double* __r
 int launch_quat_terms(vinsat_ctx* ctx, int64_t T, const double* st, const double* crot, const int32_t* gap,
                       double quat_coeff, double* drec) {
   if (T == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_DYNAMICS, k_quat_terms, ceil_div(T, 128), 128, 0, T, st, crot, gap, quat_coeff, drec);
+  VS_LAUNCH(ctx, F_QUAT, k_quat_terms, ceil_div(T, 128), 128, 0, T, st, crot, gap, quat_coeff, drec);
   return VINSAT_OK;
 }
 

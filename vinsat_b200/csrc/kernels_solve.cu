@@ -530,7 +530,7 @@ int launch_solve_retract(vinsat_batch* b, int initialize) {
   vinsat_ctx* ctx = b->ctx;
   if (b->P == 0 || b->T == 0) return VINSAT_OK;
   if (initialize) {
-    VS_LAUNCH(ctx, F_SOLVE, k_solve_init, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->lam, b->wmax,
+    VS_LAUNCH(ctx, F_SOLVE_INIT, k_solve_init, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->lam, b->wmax,
               b->grec, b->delta, b->lam32_last);
   } else {
     VS_LAUNCH(ctx, F_SOLVE, k_solve, ceil_div(b->P, kSolveWarps), kSolveWarps * 32, 0, (int)b->P, b->d_frame_off,
