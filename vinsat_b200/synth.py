@@ -132,3 +132,38 @@ def make_batch(P, T, K, seed0=0, gap_max=20, sigma_px=1.0, lm_sigma_km=60.0, pos
 
 def make_problem(seed, T, K, **kw):
     return make_batch(1, T, K, seed0=seed, **kw)[0]
+
+
+def make_sequence(seed, n_orbit=1300, windows=((5, 150, 5), (400, 520, 5), (800, 900, 5), (1150, 1230, 5)),
+                  dets_per_frame=6, sigma_px=1.0, lonlat_sigma_deg=1.0, conf_lo=0.7):
+    """A synthetic detection sequence in the reference's on-disk formats:
+      detections (n,6) rows [frame, lon_deg, lat_deg, u_px, v_px, conf] sorted by frame;
+      orbit (n_orbit,12) rows [ECEF position in metres, dir(3), up(3), right(3)], one row per second.
+    Pixels are the nadir-pointing pinhole projection of the landmark (ECI at t = frame) plus noise."""
+    rng = np.random.default_rng(seed)
+    x = hm.oe2eci_values(*random_polar_elements(rng))
+    eci = np.zeros((n_orbit, 6))
+    for t in range(n_orbit):
+        eci[t] = x
+        x = orbit_step_batch(x, 1.0)
+    times = np.arange(n_orbit, dtype=np.float64)
+    ecef = hm.eci_to_ecef(eci[:, :3], times)
+    R = hm.nadir_frames(ecef)                                   # placeholders for dir / up / right
+    orbit = np.concatenate([ecef * 1000.0, R[:, :, 2], -R[:, :, 1], -R[:, :, 0]], axis=1)
+    quat = hm.convert_pos_to_quaternion(eci[:, :3])
+    rows = []
+    for (t0, t1, step) in windows:
+        for t in range(t0, min(t1, n_orbit - 1), step):
+            p = ecef[t]
+            lon0 = np.degrees(np.arctan2(p[1], p[0]))
+            lat0 = np.degrees(np.arctan2(p[2], np.hypot(p[0], p[1])))
+            lon = lon0 + rng.normal(0, lonlat_sigma_deg, dets_per_frame) / max(np.cos(np.radians(lat0)), 0.2)
+            lat = np.clip(lat0 + rng.normal(0, lonlat_sigma_deg, dets_per_frame), -89.0, 89.0)
+            xyz = hm.convert_latlong_to_cartesian(lat, lon, np.full(dets_per_frame, float(t)))
+            st = np.concatenate([eci[t, :3], quat[t], eci[t, 3:]])[None]
+            uv = _project_truth(st, xyz, INTRINSICS_ROW0[None], np.zeros(dets_per_frame, dtype=np.int64))
+            uv = uv + rng.normal(0, sigma_px, uv.shape)
+            conf = rng.uniform(conf_lo, 1.0, dets_per_frame)
+            for k in range(dets_per_frame):
+                rows.append([float(t), lon[k], lat[k], uv[k, 0], uv[k, 1], conf[k]])
+    return np.array(rows), orbit
