@@ -1,0 +1,91 @@
+"""Driver-side indexing (a9 of SURVEY.md section 8) against the reference goldens -- integer outputs bit-exact.
+CPU only (host logic of the mirror)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from vinsat_b200 import od_pipe, trajgen_pipe
+from vinsat_b200 import hostmath as hm
+from vinsat_b200.BA import BA_utils as U
+
+SEQS = ["seq_a", "seq_b"]
+
+
+@pytest.mark.parametrize("name", SEQS)
+def test_read_detections_and_ground_truths(name):
+    g = load_golden(name)
+    orbit, ld, intr, time_idx, ii = od_pipe.read_detections(False, detections=g["dets"].copy(), orbit_np=g["orbit"].copy())
+    assert np.array_equal(time_idx, g["rd_time_idx"]) and time_idx.dtype == g["rd_time_idx"].dtype
+    assert np.array_equal(ii, g["rd_ii"])
+    assert np.array_equal(orbit, g["rd_orbit"])          # ECEF m -> ECI km, same ops as the reference
+    assert np.array_equal(intr, g["rd_intr"])
+    r = od_pipe.process_ground_truths(orbit, ld, intr, 1.0, time_idx)
+    assert np.array_equal(r[2].numpy(), g["pg_poses_gt"])
+    assert np.array_equal(r[1].numpy(), g["pg_gt_vel"])
+    assert np.array_equal(r[5].numpy(), g["pg_lm_xyz"])
+    assert np.array_equal(r[4].numpy(), g["pg_quat_full"])
+
+
+@pytest.mark.parametrize("name", SEQS)
+def test_remove_elems_and_splits(name):
+    g = load_golden(name)
+    T = len(g["rd_time_idx"])
+    dummy = torch.zeros((T, 3), dtype=torch.float64)
+    poses = torch.arange(T * 7, dtype=torch.float64).reshape(T, 7)
+    r = od_pipe.remove_elems(torch.tensor(g["vis_mask"]), dummy, dummy, poses, dummy, dummy, None, None, None, None,
+                             g["rd_ii"], g["rd_time_idx"])
+    ii_new, time_idx_new = r[9], r[10]
+    assert np.array_equal(ii_new, g["re_ii"])
+    assert np.array_equal(time_idx_new, g["re_time_idx"])
+    assert np.array_equal(r[11].numpy(), g["re_mask"])
+    assert r[2].shape[0] == len(g["re_time_idx"])
+    splits = []
+    i = t = 0
+    end = False
+    while not end:
+        t, i, end = od_pipe.identify_next_batch_new(ii_new, time_idx_new, i, t)
+        splits.append((int(t), int(i), bool(end)))
+    assert np.array_equal(np.array(splits, dtype=np.int64), g["splits"])
+
+
+def test_remove_elems_edge_cases():
+    # every observation masked out except one; knots survive; frames after the last surviving one stay
+    time_idx = np.array([3, 8, 1000, 1004, 1010, 2000, 2005])
+    ii = np.array([0, 0, 1, 3, 3, 4, 6, 6])
+    mask = torch.tensor([False, False, False, True, False, False, False, False])
+    z = torch.zeros((7, 3), dtype=torch.float64)
+    r = od_pipe.remove_elems(mask, z, z, z, z, z, None, None, None, None, ii, time_idx)
+    assert list(r[9]) == [1]                          # frames 0,1 dropped below frame 3; knot 1000 kept
+    assert list(r[10]) == [1000, 1004, 2000]
+    # empty ragged input: nothing survives
+    r = od_pipe.remove_elems(torch.zeros(8, dtype=torch.bool), z, z, z, z, z, None, None, None, None, ii, time_idx)
+    assert len(r[9]) == 0 and list(r[10]) == [1000, 2000]
+
+
+def test_host_helpers_vs_reference_golden():
+    g = load_golden("helpers")
+    eq = lambda a, b: np.abs(np.asarray(a) - b).max() <= 1e-15 * max(1.0, np.abs(b).max())
+    assert eq(U.quaternion_multiply(torch.tensor(g["q1"]), torch.tensor(g["q2"])), g["qmul"])
+    assert eq(U.quaternion_exp(torch.tensor(g["d"])), g["qexp"])
+    assert np.abs(U.quaternion_log(torch.tensor(g["q1"])).numpy() - g["qlog"]).max() < 1e-14
+    assert eq(U.attitude_jacobian(torch.tensor(g["q1"])), g["Gq"])
+    assert eq(U.precompute_cum_rotations(torch.tensor(g["omegas"]), 1.0), g["cum_rot"])
+    assert np.abs(U.compute_omega_from_quat(torch.tensor(g["qtrack"]), 1.0).numpy() - g["omega_from_quat"]).max() < 1e-12
+    assert np.array_equal(hm.convert_pos_to_quaternion(g["pos"]), g["nadir_quat"])
+    assert np.array_equal(hm.compute_velocity_from_pos(g["pos"], 1.0), g["vel_fd"])
+    assert np.array_equal(np.stack(hm.ecef_to_eci(g["pos"][:, 0], g["pos"][:, 1], g["pos"][:, 2], times=g["times"]), -1), g["ecef2eci"])
+    assert np.array_equal(hm.eci_to_ecef(g["pos"], g["times"]), g["eci2ecef"])
+    assert np.array_equal(hm.convert_latlong_to_cartesian(g["lat"], g["lon"], g["times"]), g["latlon_cart"])
+    b = torch.tensor(g["sc_b"]); idx = torch.tensor(g["sc_idx"])
+    assert np.array_equal(U.safe_scatter_add_vec(b, idx, 7).numpy(), g["sc_sum"])
+    assert np.allclose(U.safe_scatter_add_vec(b, idx, 7, mean=True).numpy(), g["sc_mean"], rtol=0, atol=1e-15)
+    # trajgen_pipe single-state helpers
+    oe = trajgen_pipe.OrbitalElements(*g["oe"]); oe2 = trajgen_pipe.OrbitalElements(*g["oe2"])
+    assert np.array_equal(trajgen_pipe.oe2eci(oe), g["oe_eci"]) and np.array_equal(trajgen_pipe.oe2eci(oe2), g["oe2_eci"])
+    assert np.array_equal(np.stack([trajgen_pipe.orbit_dynamics(x) for x in g["x"]]), g["f_np"])
+    assert np.array_equal(np.stack([trajgen_pipe.orbit_step(x, 1.0) for x in g["x"]]), g["step_np"])
+    xa = g["att_traj"][0].copy()
+    for k in range(5):
+        xa = trajgen_pipe.attitude_step(xa.copy(), 1.0)
+        assert np.abs(xa - g["att_traj"][k + 1]).max() < 1e-15

@@ -1,0 +1,252 @@
+"""Mirror of ``estimation/od_pipe.py`` (the live OD driver): ``read_detections``, ``process_ground_truths``,
+``remove_elems``, ``identify_next_batch_new``, ``streaming_version`` keep the reference's names, arguments
+and return values; the BA iterations of each streaming window run on the device (one upload per window,
+20 batched-BA calls, one download).  Citations: path:line under <reference>/estimation.
+
+The debug drivers of the reference (``od_pipe`` [stale], ``full_batch_optimization``, ``*_debugging``)
+stop in ``ipdb.set_trace()`` and are out of scope.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib, config
+from . import hostmath as hm
+from .BA.BA_filtering import BA  # noqa: F401  (same import surface as the reference)
+from .BA.BA_utils import (landmark_project, propagate_dynamics_init, quaternion_exp, quaternion_log,
+                          precompute_cum_rotations, compute_omega_from_quat, _ctx)
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+def _load_intrinsics():
+    """od_pipe.py:248 reads landmarks/intrinsics.csv relative to the cwd; fall back to the packaged copy."""
+    path = "landmarks/intrinsics.csv"
+    if not os.path.exists(path):
+        path = os.path.join(_DATA, "intrinsics.csv")
+    return np.genfromtxt(path, delimiter=",")[0]
+
+
+def seeding(seed):
+    """od_pipe.py:307-309."""
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+
+
+def read_detections(sample_dets=False, detections=None, orbit_np=None, orbit_file_name=None, detections_file_name=None):
+    """od_pipe.py:185-251.  Returns (orbit [ECI km, converted IN PLACE like the reference], landmarks_dict,
+    intrinsics row 0, time_idx with knot frames at multiples of 1000 s, ii)."""
+    landmarks = detections if detections is not None else np.load(detections_file_name, allow_pickle=True)
+    landmarks_dict = {"frame": landmarks[:, 0], "uv": landmarks[:, 3:5], "lonlat": landmarks[:, 1:3],
+                      "confidence": landmarks[:, 5]}
+    uniq, counts = np.unique(landmarks[:, 0], return_counts=True)
+    time_idx = uniq.astype(np.int64)
+    filler_idx = time_idx.min() // 1000 + 1
+    filler_offset = 0
+    time_idx_new, slots = [], []
+    for i, tidx in enumerate(time_idx):                     # :218-228
+        if tidx == filler_idx * 1000:
+            filler_idx += 1
+        while tidx > filler_idx * 1000:
+            time_idx_new.append(filler_idx * 1000)
+            filler_idx += 1
+            filler_offset += 1
+        time_idx_new.append(tidx)
+        slots.append(i + filler_offset)
+    ii = np.repeat(np.array(slots, dtype=np.int64), counts)
+    orbit = orbit_np if orbit_np is not None else np.load(orbit_file_name, allow_pickle=True)
+    orbit[:, 0], orbit[:, 1], orbit[:, 2] = hm.ecef_to_eci(orbit[:, 0] / 1000, orbit[:, 1] / 1000, orbit[:, 2] / 1000,
+                                                             times=np.arange(orbit.shape[0]))     # :240
+    if time_idx[-1] < orbit.shape[0]:                        # :242-245
+        while filler_idx * 1000 < (orbit.shape[0] // 1000) * 1000 + 1:
+            time_idx_new.append(filler_idx * 1000)
+            filler_idx += 1
+    return orbit, landmarks_dict, _load_intrinsics(), np.array(time_idx_new), ii
+
+
+def process_ground_truths(orbit, landmarks_dict, intrinsics, dt, time_idx):
+    """od_pipe.py:94-123 (nadir branch)."""
+    gt_pos_eci = orbit[time_idx, :3]
+    gt_pos_eci_full = orbit[:, :3]
+    gt_vel_eci = hm.compute_velocity_from_pos(orbit[:, :3], dt)
+    gt_quat_eci = hm.convert_pos_to_quaternion(gt_pos_eci)
+    gt_quat_eci_full = hm.convert_pos_to_quaternion(gt_pos_eci_full)
+    poses_gt_eci = np.concatenate([gt_pos_eci, gt_quat_eci], axis=1)
+    landmarks_xyz = hm.convert_latlong_to_cartesian(landmarks_dict["lonlat"][:, 1], landmarks_dict["lonlat"][:, 0],
+                                                    landmarks_dict["frame"])
+    gt_acceleration = hm.compute_velocity_from_pos(gt_vel_eci, dt)
+    t = torch.tensor
+    return (t(gt_pos_eci), t(gt_vel_eci), t(poses_gt_eci), t(gt_quat_eci), t(gt_quat_eci_full), t(landmarks_xyz),
+            t(landmarks_dict["uv"]).double(), t(intrinsics).unsqueeze(0).repeat(len(gt_pos_eci), 1),
+            t(gt_acceleration), t(gt_pos_eci_full))
+
+
+def remove_elems(mask, gt_pos_eci, gt_vel_eci, poses_gt_eci, gt_quat_eci, gt_quat_eci_full, landmarks_xyz,
+                 landmarks_uv, intrinsics, gt_acceleration, ii, time_idx):
+    """od_pipe.py:253-288 as an exclusive prefix sum over the kept-frame mask: frames kept =
+    frames with a surviving observation or knots; ii_new[k] = ii_old[k] - #{dropped frames < ii_old[k]}."""
+    mask_np = mask.numpy() if isinstance(mask, torch.Tensor) else np.asarray(mask)
+    ii_old = ii[mask_np]
+    keep = np.zeros(time_idx.shape[0], dtype=bool)
+    keep[np.unique(ii_old)] = True
+    keep |= (time_idx % 1000 == 0)
+    dropped = ~keep
+    if len(ii_old):
+        dropped[int(ii_old.max()) + 1:] = False           # the reference only walks i <= ii_old.max() (:272)
+    shift = np.concatenate([[0], np.cumsum(dropped)[:-1]])  # dropped frames strictly below each index
+    ii_new = ii_old - shift[ii_old]
+    return (gt_pos_eci[keep], gt_vel_eci, poses_gt_eci[keep], gt_quat_eci[keep], gt_quat_eci_full, landmarks_xyz,
+            landmarks_uv, intrinsics, gt_acceleration, ii_new, time_idx[keep], mask)
+
+
+def identify_next_batch_new(ii, time_idx, i, t):
+    """od_pipe.py:898-905."""
+    contiguous_patch_count = 0
+    for j in range(i + 1, len(ii)):
+        gap = time_idx[ii[j]] - time_idx[ii[j - 1]]
+        if gap < 100:
+            contiguous_patch_count += 1
+        if gap > 200 and contiguous_patch_count > 4:
+            return ii[j - 1] + 1, j, False
+    return ii[-1] + 1, len(ii), True
+
+
+def compute_residuals(states, gt_states):
+    return (states - gt_states)[..., :3].reshape(-1, 3).norm(dim=-1)
+
+
+def visibility_mask(landmark_uv_proj, landmarks_uv, confidence):
+    """od_pipe.py:930."""
+    p = landmark_uv_proj
+    return ((p[:, :, 0] > 0) * (p[:, :, 1] > 0) * (p[:, :, 0] < 4700) * (p[:, :, 1] < 2600)
+            * ((p - landmarks_uv[None]).norm(dim=-1) < 1000) * (torch.as_tensor(confidence) > 0.8))[0]
+
+
+def _window_solve(states_t, cum_rot, landmarks_uv, landmarks_xyz, ii_t, time_idx_t, intrinsics_t, confidences,
+                  lamda_init, num_iters, n_init, poses_gt_eci_t):
+    """The `for iter in range(num_iters): BA(...)` loop of one window (od_pipe.py:1035-1040) on the device:
+    one upload, num_iters batched-BA calls, one download."""
+    T, M = states_t.shape[1], len(ii_t)
+    arrays = dict(frame_off=np.array([0, T], dtype=np.int64), obs_off=np.array([0, M], dtype=np.int64),
+                  states=np.ascontiguousarray(states_t[0].numpy()), intrinsics=np.ascontiguousarray(intrinsics_t[0].numpy()),
+                  cum_rot=np.ascontiguousarray(cum_rot), time_idx=np.ascontiguousarray(time_idx_t, dtype=np.int64),
+                  landmarks_xyz=np.ascontiguousarray(landmarks_xyz[0].numpy()),
+                  landmarks_uv=np.ascontiguousarray(landmarks_uv[0].numpy()),
+                  confidences=np.ascontiguousarray(confidences.numpy()), ii=np.ascontiguousarray(ii_t, dtype=np.int64))
+    b = _lib.Batch(_ctx(), arrays)
+    lam = float(lamda_init)
+    for it in range(num_iters):
+        lam_arr, _ = b.ba_iterate(it, lam, initialize=(it < n_init), mode=config.mode())
+        lam = float(lam_arr[0])
+        if it > 18:                                            # BA_filtering.py:86-87
+            s = b.get_states()
+            d = np.abs(s[:, :3] - poses_gt_eci_t[:, :3].numpy()).mean(axis=0)
+            print("final pos: ", torch.from_numpy(d), float(np.linalg.norm(d)))
+    states_new = torch.from_numpy(b.get_states())[None]
+    last_hessian = torch.from_numpy(b.last_hessian())
+    b.close()
+    return states_new, lam, last_hessian
+
+
+def streaming_version(detections=None, orbit_np=None, orbit_file_name=None, detections_file_name=None):
+    """od_pipe.py:911-1062.  Returns (errors, first_detection, times)."""
+    seeding(0)
+    h = 1
+    dt = 1 / h
+    num_iters = 20
+    orbit, landmarks_dict, intrinsics, time_idx, ii = read_detections(False, detections=detections, orbit_np=orbit_np,
+                                                                      orbit_file_name=orbit_file_name,
+                                                                      detections_file_name=detections_file_name)
+    (gt_pos_eci, gt_vel_eci, poses_gt_eci, gt_quat_eci, gt_quat_eci_full, landmarks_xyz, landmarks_uv, intrinsics,
+     gt_acceleration, gt_pos_eci_full) = process_ground_truths(orbit, landmarks_dict, intrinsics, dt, time_idx)
+    states_gt_eci = torch.cat([poses_gt_eci, gt_vel_eci[time_idx]], dim=-1)
+    landmark_uv_proj = landmark_project(states_gt_eci.unsqueeze(0), landmarks_xyz.unsqueeze(0), intrinsics.unsqueeze(0),
+                                        ii, jacobian=False)
+    mask = visibility_mask(landmark_uv_proj, landmarks_uv, landmarks_dict["confidence"])
+    (gt_pos_eci, gt_vel_eci, poses_gt_eci, gt_quat_eci, gt_quat_eci_full, landmarks_xyz, landmarks_uv, intrinsics,
+     gt_acceleration, ii, time_idx, mask) = remove_elems(mask, gt_pos_eci, gt_vel_eci, poses_gt_eci, gt_quat_eci,
+                                                         gt_quat_eci_full, landmarks_xyz, landmarks_uv, intrinsics,
+                                                         gt_acceleration, ii, time_idx)
+    landmarks_xyz, landmarks_uv, landmark_uv_proj = landmarks_xyz[mask], landmarks_uv[mask], landmark_uv_proj[:, mask]
+    confidences = torch.tensor(landmarks_dict["confidence"])[mask].double()
+    print("mean landmark difference : ", ((landmark_uv_proj[0, :] - landmarks_uv)).abs().mean(dim=0))
+    noise_level = 1.0
+    landmarks_uv += (landmark_uv_proj[0, :] - landmarks_uv) * (1 - noise_level)
+
+    # initial guess (od_pipe.py:941-973); the torch RNG call order is the reference's
+    T = len(gt_pos_eci)
+    N = max(time_idx[1:] - time_idx[:-1])
+    gt_omega = compute_omega_from_quat(gt_quat_eci_full, dt)
+    velocities = gt_vel_eci[time_idx].unsqueeze(0).double()
+    omegas = torch.zeros((1, T, N, 3)).double()
+    for i in range(1, T):
+        omegas[:, i - 1, :time_idx[i] - time_idx[i - 1], :] = gt_omega[time_idx[i - 1]:time_idx[i], :].unsqueeze(0).double()
+    cum_rot = precompute_cum_rotations(omegas, dt)[0, :, -1].numpy()      # the only slice `predict` reads
+    position_offset = torch.randn((T, 3)) * 100
+    orientation_offset = torch.randn([T, 3]) * 0.2
+    velocity_offset = torch.randn([T, 3]) * velocities.abs().mean() * 0.1
+    position = poses_gt_eci.double()[:, :3] + position_offset
+    orientation = quaternion_exp(quaternion_log(poses_gt_eci.double()[:, 3:]) + orientation_offset)
+    vels = velocities.double() + velocity_offset.unsqueeze(0)
+    poses = torch.cat([position, orientation], dim=1).unsqueeze(0)
+    states = torch.cat([poses, vels], dim=-1)
+    landmarks_uv = landmarks_uv.unsqueeze(0)
+    landmarks_xyz = landmarks_xyz.unsqueeze(0)
+    intrinsics = intrinsics.unsqueeze(0)
+    lamda_init = 1e-4
+
+    t = 0
+    i = 0
+    seq_end = False
+    patch_id = 0
+    errors, times = [], []
+    first_detection = None
+    while not seq_end:                                         # od_pipe.py:987
+        t_init, i_init = t, i
+        t_final, i_final, seq_end = identify_next_batch_new(ii, time_idx, i, t)
+        t, i = t_final, i_final
+        if patch_id == 0:
+            states_t = states[:, :t_final]
+            velocities_t = velocities[:, :t_final]
+            time_idx_t = time_idx[:t_final]
+            poses_gt_eci_t = poses_gt_eci[:t_final]
+            first_detection = time_idx_t[-1]
+        else:
+            omega = gt_omega[time_idx[t_init - 1]:time_idx[t_final - 1]].unsqueeze(0).double()
+            tdiff = time_idx[t_init] - time_idx[t_init - 1]
+            duration = time_idx[t_final - 1] - time_idx[t_init]
+            states_prop, velocities_prop, _, _ = propagate_dynamics_init(states_t[:, -1], velocities_t[:, -1], omega,
+                                                                         int(tdiff), int(duration), 1)
+            time_idx_prop = time_idx[t_init:t_final]
+            sel = time_idx_prop - time_idx_prop[0]
+            states_prop, velocities_prop = states_prop[:, sel], velocities_prop[:, sel]
+            time_idx_t = time_idx[:t_final]
+            poses_gt_eci_t = poses_gt_eci[:t_final]
+            states_t = torch.cat([states_t, states_prop], dim=1)
+            velocities_t = torch.cat([velocities_t, velocities_prop], dim=1)
+            error_prop = compute_residuals(states_prop[0][:, :3], poses_gt_eci_t[-states_prop.shape[1]:, :3])[:-1]
+            times.append(time_idx_t[-states_prop.shape[1]:][:-1])
+            errors.append(error_prop)
+        states_t, _, _ = _window_solve(states_t, cum_rot[:t_final], landmarks_uv[:, :i_final], landmarks_xyz[:, :i_final],
+                                       ii[:i_final], time_idx_t, intrinsics[:, :t_final], confidences[:i_final],
+                                       lamda_init, num_iters, 10 if patch_id == 0 else 0, poses_gt_eci_t)
+        patch_id += 1
+        error_t = (states_t[..., :3].reshape(-1, 3)[-1:] - poses_gt_eci_t[-1:, :3]).norm(dim=-1)
+        errors.append(error_t)
+        times.append(time_idx_t[-1:])
+        if seq_end and t_final < len(time_idx):                # od_pipe.py:1046-1060
+            t_init = t_final
+            t_final = len(time_idx)
+            omega = gt_omega[time_idx[t_init - 1]:time_idx[t_final - 1]].unsqueeze(0).double()
+            tdiff = time_idx[t_init] - time_idx[t_init - 1]
+            duration = time_idx[t_final - 1] - time_idx[t_init]
+            states_prop, _, _, _ = propagate_dynamics_init(states_t[:, -1], velocities_t[:, -1], omega, int(tdiff),
+                                                           int(duration), 1)
+            time_idx_prop = time_idx[t_init:t_final]
+            states_prop = states_prop[:, time_idx_prop - time_idx_prop[0]]
+            poses_gt_eci_tail = poses_gt_eci[t_init:t_final]
+            errors.append(compute_residuals(states_prop[0][:, :3], poses_gt_eci_tail[-states_prop.shape[1]:, :3]))
+            times.append(time_idx[-states_prop.shape[1]:])
+    errors = torch.cat(errors)
+    return errors, first_detection, times
