@@ -154,6 +154,9 @@ def run_reference(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    # NCCL / torchrun chatter goes to fd 1; keep stdout clean for the ONE JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from vinsat_b200 import _lib, synth
@@ -301,7 +304,7 @@ def run_gpu(args):
                                    "landmark obs/frame per GPU; one step = 20 BA iterations (10 initialize + 10 full) per problem" % (P, T, K),
                        **w, "problems_total": world * P, "l2_policy": "inputs larger than L2 (per-step working set %.1f GB per GPU)"
                        % ((batch.T * 3200 + batch.M * 100) / 1e9), "propagator": "step1s (reference CPU `predict`)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes) * world, "d2h_bytes_per_step": int(d2h_bytes) * world,
                     "ms_per_step": 1e3 * e2e_wall_s / args.steps, "timing": "wall clock, barrier+synchronize both sides, max over ranks"},
             "gpu_launches": total_launches,
             "clocks": clocks,
@@ -314,7 +317,7 @@ def run_gpu(args):
                 "max_pos_err_vs_truth_km": err,
             },
         }
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     batch.close()
     ctx.close()
     if world > 1:
