@@ -286,3 +286,40 @@ def test_satcam_projection_and_visibility_bit_exact(ctx):
 def test_device_peaks_measurable(ctx):
     assert ctx.fp64_peak_tflops() > 1.0
     assert ctx.copy_bw_gbs(1 << 28) > 100.0
+
+
+# ------------------------------------------------------------------ partitioned block-tridiagonal solve
+@pytest.mark.parametrize("seg_len", [1, 2, 5, 7, 13, 1000])
+def test_partitioned_solve_matches_oracle(ctx, monkeypatch, seg_len):
+    """The segment/separator decomposition (kernels_chain.cu) must give the same step as the dense solve,
+    for every segment length (1 = every frame is a separator, 1000 = unpartitioned)."""
+    monkeypatch.setenv("VINSAT_SEG_LEN", str(seg_len))
+    prs = [synth.make_problem(31, 41, 7), synth.make_problem(32, 18, 5), synth.make_problem(33, 1, 4),
+           synth.make_problem(34, 2, 3)]
+    arrays = _lib.concat_problems(prs)
+    for it, init in ((12, False), (15, False)):
+        b = _lib.Batch(ctx, arrays)
+        lam, ntr = b.ba_iterate(it, 1e-4, initialize=init)
+        dbg = b.debug_fetch()
+        for p, pr in enumerate(prs):
+            f0, f1 = arrays["frame_off"][p], arrays["frame_off"][p + 1]
+            _, lam_o, _, info = o.ba_iteration(it, pr["states0"], pr["cum_rot"], pr["uv"], pr["xyz"], pr["ii"],
+                                               pr["time_idx"], pr["intr"], pr["conf"], 1e-4, initialize=init, dense=True)
+            assert ntr[p] == info["ntrials"] and lam[p] == lam_o
+            if ntr[p] == 1:
+                # backward-stability criterion on the oracle's dense matrix (cond ~1e11..1e12, SURVEY 0.10) ...
+                Ad = o.dense_from_blocks(info["Dg"], info["U"], info["lam32"])
+                x = dbg["dpose"][f0:f1].reshape(-1)
+                res = np.abs(Ad @ x - info["b"].reshape(-1)).max()
+                assert res < 1e-11 * (np.abs(Ad).sum(1).max() * np.abs(x).max() + np.abs(info["b"]).max()), (seg_len, p, res)
+                # ... and the step itself to 1e-3 relative (1e-6 for the well-conditioned larger problems)
+                scale = max(1.0, np.abs(info["dpose"]).max())
+                tol = 1e-6 if f1 - f0 > 10 else 1e-3
+                assert np.abs(dbg["dpose"][f0:f1] - info["dpose"]).max() < tol * scale, (seg_len, p)
+        b.close()
+
+
+@pytest.mark.parametrize("seg_len", [6, 25])
+def test_partitioned_od_solve_tracks_reference(ctx, monkeypatch, seg_len):
+    monkeypatch.setenv("VINSAT_SEG_LEN", str(seg_len))
+    _run_batch_vs_golden(ctx, BA_CASES)

@@ -32,7 +32,9 @@ void free_all(vinsat_batch* b) {
   void* ptrs[] = {b->st, b->st_new, b->intr, b->crot, b->gap, b->fprob, b->dyn_order, b->obs_start, b->grec, b->drec,
                   b->srec, b->wrec, b->delta, b->e_obs, b->e_dyn, b->X, b->uv, b->conf, b->oframe, b->r, b->wu, b->J,
                   b->d_frame_off, b->d_obs_off, b->c_obs, b->wmax, b->lam, b->lam_next, b->lam32_last, b->init_res,
-                  b->active, b->ntrials, b->sel_prefix, b->sel_rank, b->sel_hist, b->flags};
+                  b->active, b->ntrials, b->sel_prefix, b->sel_rank, b->sel_hist, b->flags, b->seg_a, b->seg_b,
+                  b->seg_left, b->seg_prob, b->seg_has_next, b->pl_a, b->pl_b, b->pl_prob, b->red_a, b->red_b,
+                  b->redrec, b->rsys, b->rlow, b->rwrec};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (b->h_flags) cudaFreeHost(b->h_flags);
@@ -92,6 +94,46 @@ int build_frame_index(vinsat_batch* b, const vinsat_problem_desc* d, std::vector
   return VINSAT_OK;
 }
 
+// Cut every problem into segments for the partitioned solve (kernels_chain.cu).  Depends only on frame_off.
+struct Segmentation {
+  std::vector<int32_t> a, b, left, prob, has_next, pl_a, pl_b, pl_prob, red_a, red_b;
+  bool partitioned = false;
+};
+
+Segmentation make_segments(const vinsat_ctx* ctx, int64_t P, const int64_t* frame_off) {
+  Segmentation s;
+  const int64_t T = frame_off[P];
+  int64_t forced = 0;
+  if (const char* e = getenv("VINSAT_SEG_LEN")) forced = atoll(e);
+  const double target_chains = 8.0 * ctx->sm_count * 4;      // ~8 warps of 4 chains per SM
+  for (int64_t p = 0; p < P; p++) {
+    const int64_t f0 = frame_off[p], f1 = frame_off[p + 1], Tp = f1 - f0;
+    s.pl_a.push_back((int32_t)f0); s.pl_b.push_back((int32_t)f1); s.pl_prob.push_back((int32_t)p);
+    s.red_a.push_back((int32_t)s.a.size());
+    if (Tp > 0) {
+      int64_t S;
+      if (forced > 0) S = (Tp + forced - 1) / forced;
+      else {
+        S = (int64_t)llround((double)Tp * target_chains / (double)std::max<int64_t>(T, 1));
+        S = std::min<int64_t>(S, (int64_t)sqrt((double)Tp));
+        if (Tp < 64) S = 1;
+      }
+      S = std::max<int64_t>(1, std::min<int64_t>(S, Tp));
+      if (S > 1) s.partitioned = true;
+      for (int64_t k = 0; k < S; k++) {
+        const int64_t lo = f0 + (Tp * k) / S, hi = f0 + (Tp * (k + 1)) / S;   // frames [lo, hi), separator hi-1
+        s.a.push_back((int32_t)lo);
+        s.b.push_back((int32_t)(hi - 1));
+        s.left.push_back(k > 0 ? (int32_t)(lo - 1) : -1);
+        s.prob.push_back((int32_t)p);
+        s.has_next.push_back(k + 1 < S ? 1 : 0);
+      }
+    }
+    s.red_b.push_back((int32_t)s.a.size());
+  }
+  return s;
+}
+
 int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
   vinsat_ctx* ctx = b->ctx;
   VS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -114,6 +156,20 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
   VS_CUDA(ctx, cudaMemcpyAsync(b->st, d->states, T * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
   VS_CUDA(ctx, cudaMemcpyAsync(b->intr, d->intrinsics, T * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
   VS_CUDA(ctx, cudaMemcpyAsync(b->crot, d->cum_rot, T * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  {
+    Segmentation sg = make_segments(ctx, P, d->frame_off);
+    if ((int64_t)sg.a.size() != b->n_seg)
+      return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_upload: segmentation differs (frame_off must not change)");
+    b->partitioned = sg.partitioned;
+    auto up = [&](int32_t* dst, const std::vector<int32_t>& v) {
+      return v.empty() ? cudaSuccess : cudaMemcpyAsync(dst, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s);
+    };
+    VS_CUDA(ctx, up(b->seg_a, sg.a)); VS_CUDA(ctx, up(b->seg_b, sg.b)); VS_CUDA(ctx, up(b->seg_left, sg.left));
+    VS_CUDA(ctx, up(b->seg_prob, sg.prob)); VS_CUDA(ctx, up(b->seg_has_next, sg.has_next));
+    VS_CUDA(ctx, up(b->pl_a, sg.pl_a)); VS_CUDA(ctx, up(b->pl_b, sg.pl_b)); VS_CUDA(ctx, up(b->pl_prob, sg.pl_prob));
+    VS_CUDA(ctx, up(b->red_a, sg.red_a)); VS_CUDA(ctx, up(b->red_b, sg.red_b));
+    VS_CUDA(ctx, cudaStreamSynchronize(s));     // the host vectors die at the end of this scope
+  }
   VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, 4 * sizeof(int32_t), s));
   if (M > 0) {
     // stage AoS observation arrays + ii in scratch, then transpose to SoA / index on the device
@@ -156,8 +212,13 @@ int vinsat_batch_create(vinsat_ctx* ctx, const vinsat_problem_desc* d, vinsat_ba
   b->T = d->frame_off[b->P];
   b->M = d->obs_off[b->P];
   const int64_t P = b->P, T = b->T, M = b->M;
+  b->n_seg = (int64_t)make_segments(ctx, P, d->frame_off).a.size();
+  const int64_t NS = b->n_seg;
   int rc = VINSAT_OK;
 #define A(ptr, n) if (rc == VINSAT_OK) rc = dev_alloc(ctx, &b->ptr, (n))
+  A(seg_a, NS); A(seg_b, NS); A(seg_left, NS); A(seg_prob, NS); A(seg_has_next, NS);
+  A(pl_a, P); A(pl_b, P); A(pl_prob, P); A(red_a, P); A(red_b, P);
+  A(redrec, NS * VS_RREC); A(rsys, NS * VS_SREC); A(rlow, NS * 81); A(rwrec, NS * VS_WREC);
   A(st, T * 10); A(st_new, T * 10); A(intr, T * 4); A(crot, T * 4); A(gap, T); A(fprob, T); A(dyn_order, T);
   A(obs_start, T + 1); A(grec, T * VS_GREC); A(drec, T * VS_DREC); A(srec, T * VS_SREC); A(wrec, T * VS_WREC);
   A(delta, T * 9); A(e_obs, T); A(e_dyn, T);

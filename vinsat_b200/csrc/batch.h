@@ -6,7 +6,8 @@
 #define VS_GREC 28    // obs normal block: 21 sym (6x6 upper) + 6 rhs + 1 sum|r|
 #define VS_DREC 64    // dynamics: Phi 36 | r6 6 | rho 1 | qgrad 3 | Hq_diag 9 | Hq_off 9
 #define VS_SREC 172   // system: D 81 | U 81 | b 9 | pad 1
-#define VS_WREC 90    // solver: W = S^-1 U (col-major 81) | y 9
+#define VS_WREC 172   // solver: W = S^-1 U (col-major 81) | y 9 | Z spike (col-major 81) | pad
+#define VS_RREC 342   // reduced-system contributions of a segment: left {Dl 81, Ll 81, bl 9} | right {Dr 81, Ur 81, br 9}
 
 struct vinsat_batch {
   vinsat_ctx* ctx = nullptr;
@@ -29,6 +30,16 @@ struct vinsat_batch {
   double* srec = nullptr;      // [T][VS_SREC]
   double* wrec = nullptr;      // [T][VS_WREC]
   double* delta = nullptr;     // [T][9]
+  // ---- partitioned block-tridiagonal solve (kernels_chain.cu) ----
+  bool partitioned = false;
+  int64_t n_seg = 0;
+  int32_t *seg_a = nullptr, *seg_b = nullptr, *seg_left = nullptr, *seg_prob = nullptr, *seg_has_next = nullptr;  // [n_seg]
+  int32_t *pl_a = nullptr, *pl_b = nullptr, *pl_prob = nullptr;   // [P] whole-problem chains
+  int32_t *red_a = nullptr, *red_b = nullptr;                     // [P] reduced chains (segment index ranges)
+  double* redrec = nullptr;    // [n_seg][VS_RREC]
+  double* rsys = nullptr;      // [n_seg][VS_SREC] reduced system rows
+  double* rlow = nullptr;      // [n_seg][81] explicit lower blocks of the reduced system
+  double* rwrec = nullptr;     // [n_seg][VS_WREC]
   double* e_obs = nullptr;     // [T] trial partial sums (obs part)
   double* e_dyn = nullptr;     // [T] trial partial sums (dynamics part)
   // ---- device, per observation (SoA) ----

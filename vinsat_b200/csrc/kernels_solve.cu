@@ -299,149 +299,6 @@ int launch_accept(vinsat_batch* b, int initialize, double Sigma) {
   return VINSAT_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// batched block-tridiagonal LU solve (BA_filtering.py:54-55).  One warp per problem.
-//
-// Forward sweep, frame i: the augmented 9x19 block [S_i | U_i | b~_i] is held one COLUMN per lane
-// (lanes 0..18, 9 registers each); Gauss-Jordan without pivoting (the symmetric part of S_i is positive
-// definite) broadcasts the pivot column through shared memory.  Afterwards lanes 9..17 hold
-// W_i = S_i^-1 U_i and lane 18 holds y_i = S_i^-1 b~_i; S_{i+1} = D_{i+1} + lam I - U_i^T W_i and
-// b~_{i+1} = b_{i+1} - U_i^T y_i.  Backward sweep: delta_i = y_i - W_i delta_{i+1}.
-// The sweep is a latency chain (T dependent 9x9 eliminations), so global loads are software-prefetched one
-// frame ahead and the pivot reciprocal uses rcp.approx + two Newton steps instead of an IEEE division.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kSolveWarps = 1;
-
-__device__ __forceinline__ double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
-}
-
-__global__ void __launch_bounds__(kSolveWarps * 32) k_solve(int P, const int64_t* __restrict__ frame_off,
-                                                           const int32_t* __restrict__ active,
-                                                           const double* __restrict__ lam,
-                                                           const double* __restrict__ srec,
-                                                           double* __restrict__ wrec, double* __restrict__ delta,
-                                                           double* __restrict__ lam32_last) {
-  __shared__ double s_col[kSolveWarps][2][9];
-  __shared__ double s_U[kSolveWarps][81];
-  __shared__ double s_W[kSolveWarps][90];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p = blockIdx.x * kSolveWarps + warp;
-  if (p >= P) return;
-  if (!active[p]) return;
-  const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
-  if (f1 <= f0) return;
-  const double lam32 = (double)(float)lam[p];       // torch.eye(n)*lamda is float32
-  if (lane == 0) lam32_last[p] = lam32;
-  const int c = lane;
-  // offset of element (r, c) inside a system record
-  const int base = c < 9 ? c : (c < 18 ? 81 + (c - 9) : 162);
-  const int rstride = c < 18 ? 9 : 1;
-  double a[9], nxt[9], corr[9];
-#pragma unroll
-  for (int r = 0; r < 9; r++) { corr[r] = 0.0; nxt[r] = 0.0; }
-  if (c < 19) {
-    const double* rec = srec + f0 * VS_SREC;
-#pragma unroll
-    for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
-  }
-  double (*colk)[9] = s_col[warp];
-  double* Us = s_U[warp];
-  double* Ws = s_W[warp];
-  for (int64_t f = f0; f < f1; f++) {
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-      double v = nxt[r];
-      if (c < 9) v += (r == c ? lam32 : 0.0) - corr[r];
-      else if (c == 18) v -= corr[r];
-      a[r] = v;
-    }
-    if (f + 1 < f1 && c < 19) {
-      const double* rec = srec + (f + 1) * VS_SREC;
-#pragma unroll
-      for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
-    }
-    if (c >= 9 && c < 18) {
-#pragma unroll
-      for (int r = 0; r < 9; r++) Us[r * 9 + (c - 9)] = a[r];
-    }
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-      if (c == k) {
-#pragma unroll
-        for (int r = 0; r < 9; r++) colk[k & 1][r] = a[r];
-      }
-      __syncwarp();
-      double pk[9];
-#pragma unroll
-      for (int r = 0; r < 9; r++) pk[r] = colk[k & 1][r];
-      const double pr = a[k] * fast_rcp(pk[k]);
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        if (r == k) a[r] = pr;
-        else a[r] = fma(-pk[r], pr, a[r]);
-      }
-    }
-    if (c >= 9 && c < 19) {
-      double* w = wrec + f * VS_WREC + (c - 9) * 9;
-#pragma unroll
-      for (int r = 0; r < 9; r++) { w[r] = a[r]; Ws[(c - 9) * 9 + r] = a[r]; }
-    }
-    __syncwarp();
-    if (f + 1 < f1 && (c < 9 || c == 18)) {
-      const double* wc = Ws + (c < 9 ? c : 9) * 9;
-      double wv[9];
-#pragma unroll
-      for (int k = 0; k < 9; k++) wv[k] = wc[k];
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < 9; k++) s = fma(Us[k * 9 + r], wv[k], s);
-        corr[r] = s;
-      }
-    }
-    __syncwarp();
-  }
-  // backward sweep: lane r < 9 owns row r; the next record is prefetched while the current one is used
-  double dn[9], wcur[10], wnx[10];
-#pragma unroll
-  for (int k = 0; k < 9; k++) dn[k] = 0.0;
-#pragma unroll
-  for (int k = 0; k < 10; k++) { wcur[k] = 0.0; wnx[k] = 0.0; }
-  const int lr = lane < 9 ? lane : 0;
-  {
-    const double* w = wrec + (f1 - 1) * VS_WREC;
-#pragma unroll
-    for (int k = 0; k < 9; k++) wnx[k] = w[k * 9 + lr];
-    wnx[9] = w[81 + lr];
-  }
-  for (int64_t f = f1 - 1; f >= f0; f--) {
-#pragma unroll
-    for (int k = 0; k < 10; k++) wcur[k] = wnx[k];
-    if (f > f0) {
-      const double* w = wrec + (f - 1) * VS_WREC;
-#pragma unroll
-      for (int k = 0; k < 9; k++) wnx[k] = w[k * 9 + lr];
-      wnx[9] = w[81 + lr];
-    }
-    double dr = wcur[9];
-    if (f + 1 < f1) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) dr = fma(-wcur[k], dn[k], dr);
-    }
-#pragma unroll
-    for (int k = 0; k < 9; k++) dn[k] = __shfl_sync(0xffffffffu, dr, k);
-    if (lane < 9) delta[f * 9 + lane] = dr;
-  }
-}
-
 // initialize phase (BA_utils.py:463-466 => no dynamics terms): the system is block diagonal, every frame is
 // an independent SPD 6x6 pose block (+ lam I) and three decoupled velocity rows with zero right-hand side.
 // One thread per frame, Cholesky in registers, straight from the observation record (no srec round trip).
@@ -533,8 +390,8 @@ int launch_solve_retract(vinsat_batch* b, int initialize) {
     VS_LAUNCH(ctx, F_SOLVE_INIT, k_solve_init, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->lam, b->wmax,
               b->grec, b->delta, b->lam32_last);
   } else {
-    VS_LAUNCH(ctx, F_SOLVE, k_solve, ceil_div(b->P, kSolveWarps), kSolveWarps * 32, 0, (int)b->P, b->d_frame_off,
-              b->active, b->lam, b->srec, b->wrec, b->delta, b->lam32_last);
+    int rc = launch_chain_solve(b);
+    if (rc != VINSAT_OK) return rc;
   }
   VS_LAUNCH(ctx, F_RETRACT, k_retract, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->st, b->delta,
             b->st_new);

@@ -46,4 +46,7 @@ int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double l
 int launch_solve_retract(vinsat_batch* b, int initialize);
 int launch_accept(vinsat_batch* b, int initialize, double Sigma);
 
+// ---- kernels_chain.cu -------------------------------------------------------------------------------
+int launch_chain_solve(vinsat_batch* b);   // delta = A^-1 rhs for every active problem (partitioned block LU)
+
 }  // namespace vs
