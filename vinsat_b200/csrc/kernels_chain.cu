@@ -11,19 +11,18 @@
 // small block-tridiagonal REDUCED system (one 9x9 row per segment) which the same elimination solves (plain
 // mode, explicit lower blocks).  A last pass back-substitutes the interiors.
 //
-// Mapping: 8 lanes per chain, 4 chains per warp.  The augmented block [S | U | b | Z] (9 x 28) is held by
-// COLUMNS: lane l of a group owns (S_l, U_l, Z_l) and lanes 0..3 own one extra column each (S_8, U_8, Z_8, b).
-// Gauss-Jordan without pivoting (the symmetric part of every pivot block is positive definite):
-// the pivot column is broadcast with group shuffles, every lane then updates its 3-4 columns (24-32
-// independent DFMAs per step), so all 32 lanes do useful FP64 work and the kernel is FP64-pipe / latency
-// bound instead of issue bound.
+// Mapping: ONE WARP PER CHAIN.  The augmented block [S | U | b | Z] (9 x 28) is held one COLUMN per lane
+// (lanes 0-8 S, 9-17 U, 18 b, 19-27 Z; 9 registers each), so control flow is uniform inside a warp and the
+// code stays small enough for the instruction cache (a first version with 4 chains per warp compiled to
+// 84 KB of SASS and was instruction-fetch bound).  Gauss-Jordan without pivoting (the symmetric part of every
+// pivot block is positive definite); the pivot column is broadcast through shared memory.
+// Parallelism comes from the number of chains (P x segments), ~35 resident warps per SM at P = 1024.
 #include "common.cuh"
 #include "launch.h"
 
 namespace vs {
 
-constexpr int kGL = 8;            // lanes per chain
-constexpr int kCPW = 32 / kGL;    // chains per warp
+constexpr int kMS = 10;   // padded row stride of 9x9 blocks in shared memory (16-byte aligned rows)
 
 __device__ __forceinline__ double fast_rcp_c(double x) {
   double r;
@@ -35,17 +34,21 @@ __device__ __forceinline__ double fast_rcp_c(double x) {
   return r;
 }
 
-__device__ __forceinline__ double gshfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src, kGL); }
-
-// out[r] = sum_k M[k*9 + r] * v[k]   (M in shared memory, broadcast reads)
+// out[r] = sum_k M[k*kMS + r] * v[k]   (M in shared memory, all lanes read the same addresses)
 __device__ __forceinline__ void matvec9(const double* __restrict__ M, const double* v, double* out) {
 #pragma unroll
   for (int r = 0; r < 9; r++) out[r] = 0.0;
 #pragma unroll
   for (int k = 0; k < 9; k++) {
     const double vk = v[k];
+    const double2* row = reinterpret_cast<const double2*>(M + k * kMS);
 #pragma unroll
-    for (int r = 0; r < 9; r++) out[r] = fma(M[k * 9 + r], vk, out[r]);
+    for (int r2 = 0; r2 < 4; r2++) {
+      const double2 m = row[r2];
+      out[2 * r2] = fma(m.x, vk, out[2 * r2]);
+      out[2 * r2 + 1] = fma(m.y, vk, out[2 * r2 + 1]);
+    }
+    out[8] = fma(M[k * kMS + 8], vk, out[8]);
   }
 }
 
@@ -61,286 +64,269 @@ struct ChainArgs {
   const double* lrec;        // explicit lower blocks: lrec[i] = A(i+1,i) row-major, or null (=> U_i^T)
   double* wrec;              // [n][VS_WREC]  W (col-major) | y | Z (col-major)
   double* redrec;            // SEG: [n_chains][VS_RREC] contributions to the reduced system
-  double* delta;             // PLAIN: solution rows; SEG back-substitution: in/out
+  double* delta;             // solution rows
   const int32_t* out_index;  // PLAIN: element -> row of delta (null = identity)
   double* lam32_last;        // [P] or null
 };
 
+constexpr int kFwdWarps = 4;
+
 // ---------------------------------------------------------------------------------------------------------
-// forward elimination of one chain per 8-lane group.  SPIKE=true: segment mode.
+// forward elimination of one chain per warp.  SPIKE=true: segment mode (Z columns + left-part record).
 // ---------------------------------------------------------------------------------------------------------
 template <bool SPIKE>
-__global__ void __launch_bounds__(32) k_chain(ChainArgs A) {
-  __shared__ double s_M[kCPW][81];
-  __shared__ double s_W[kCPW][81];
-  const int lane = threadIdx.x & 31;
-  const int g = lane / kGL, gl = lane % kGL;
-  const int ch = blockIdx.x * kCPW + g;
-  const bool valid = ch < A.n_chains;
-  int a = 0, e = 0, left = -1, prob = 0;
-  bool live = false;
-  if (valid) {
-    a = A.ch_a[ch]; e = A.ch_b[ch]; prob = A.ch_prob[ch];
-    if (SPIKE) left = A.ch_left[ch];
-    live = A.active ? (A.active[prob] != 0) : true;
-  }
-  if (!live) { a = 0; e = 0; left = -1; }
+__global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
+  __shared__ __align__(16) double s_col[kFwdWarps][2][kMS];
+  __shared__ __align__(16) double s_M[kFwdWarps][9 * kMS];
+  __shared__ __align__(16) double s_W[kFwdWarps][10 * 9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * kFwdWarps + warp;
+  if (ch >= A.n_chains) return;
+  const int prob = A.ch_prob[ch];
+  if (A.active && !A.active[prob]) return;
+  const int a = A.ch_a[ch], e = A.ch_b[ch];
+  const int left = SPIKE ? A.ch_left[ch] : -1;
   double lam32 = 0.0;
-  if (live && A.lam) {
+  if (A.lam) {
     lam32 = (double)(float)A.lam[prob];           // torch.eye(n)*lamda is float32
-    if (A.lam32_last && gl == 0) A.lam32_last[prob] = lam32;
+    if (A.lam32_last && lane == 0) A.lam32_last[prob] = lam32;
   }
-  // the groups of a warp run in lock step over max(len)
-  int len = e - a;
-  int maxlen = len;
-#pragma unroll
-  for (int o = 16; o >= kGL; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-  double* M = s_M[g];
-  double* Wst = s_W[g];
-  const bool has_x = gl < 4;                      // owns an extra column: 0:S_8 1:U_8 2:Z_8 3:b
-  double c0[9], c1[9], c2[9], c3[9];
-  double n0[9], n1[9], n3[9];
-#pragma unroll
-  for (int r = 0; r < 9; r++) { c0[r] = c1[r] = c2[r] = c3[r] = 0.0; n0[r] = n1[r] = n3[r] = 0.0; }
+  const int c = lane;
+  // column roles
+  const bool isS = c < 9, isU = c >= 9 && c < 18, isB = c == 18, isZ = SPIKE && c >= 19 && c < 28;
+  const int cc = isS ? c : (isU ? c - 9 : (isZ ? c - 19 : 0));       // column index inside its block
+  // offset of element (r, c) inside a system record
+  const int base = isS ? c : (isU ? 81 + (c - 9) : 162);
+  const int rstride = isB ? 1 : 9;
+  const bool loads = isS || isU || isB;
+  double (*colk)[kMS] = s_col[warp];
+  double* M = s_M[warp];
+  double* Ws = s_W[warp];
+  double* rr = SPIKE ? A.redrec + (int64_t)ch * VS_RREC : nullptr;
+  const int len = e - a;
 
-  auto load_cols = [&](int i, double* d0, double* d1, double* d3) {
-    const double* rec = A.rec + (int64_t)i * VS_SREC;
+  if (SPIKE && len == 0) {
+    // no interior: the separator couples directly to the left separator.  Ll = Lo_left, Dl = bl = 0.
+    for (int idx = lane; idx < 171; idx += 32) {
+      double v = 0.0;
+      if (idx >= 81 && idx < 162 && left >= 0) {
+        const int r = (idx - 81) / 9, k = (idx - 81) % 9;
+        v = A.lrec ? A.lrec[(int64_t)left * 81 + r * 9 + k] : A.rec[(int64_t)left * VS_SREC + 81 + k * 9 + r];
+      }
+      rr[idx] = v;
+    }
+    return;
+  }
+  if (len <= 0) return;
+
+  double a_[9], nxt[9], corr[9];
+#pragma unroll
+  for (int r = 0; r < 9; r++) { corr[r] = 0.0; nxt[r] = 0.0; a_[r] = 0.0; }
+  if (loads) {
+    const double* rec = A.rec + (int64_t)a * VS_SREC;
+#pragma unroll
+    for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
+  }
+  if (isZ && left >= 0) {
+    // Z~_a = Lo_left: column cc.  explicit: Lo[r][cc]; base: Lo[r][cc] = U_left[cc][r].  Stored NEGATED in corr
+    // because the assembly below uses a = nxt - corr.
+    if (A.lrec) {
+#pragma unroll
+      for (int r = 0; r < 9; r++) corr[r] = -A.lrec[(int64_t)left * 81 + r * 9 + cc];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 9; r++) corr[r] = -A.rec[(int64_t)left * VS_SREC + 81 + cc * 9 + r];
+    }
+  }
+
+  for (int i = a; i < e; i++) {
+    // assemble the augmented column of element i:  S: D + lam I - Lo W;  U: fresh;  b: b - Lo y;  Z: -Lo Z
 #pragma unroll
     for (int r = 0; r < 9; r++) {
-      d0[r] = rec[r * 9 + gl];
-      d1[r] = rec[81 + r * 9 + gl];
-      double x = 0.0;
-      if (gl == 0) x = rec[r * 9 + 8];
-      else if (gl == 1) x = rec[81 + r * 9 + 8];
-      else if (gl == 3) x = rec[162 + r];
-      d3[r] = x;
+      double v = nxt[r];
+      if (isS) v += (r == c ? lam32 : 0.0) - corr[r];
+      else if (isB || isZ) v -= corr[r];
+      a_[r] = v;
     }
-  };
-
-  if (len > 0) {
-    load_cols(a, n0, n1, n3);
-    if (SPIKE && left >= 0) {
-      // Z~_a = Lo_left : column c of Lo_left.  lrec: Lo[r][c] ; base: Lo[r][c] = U_left[c][r]
-      if (A.lrec) {
-        const double* L = A.lrec + (int64_t)left * 81;
+    if (i + 1 < e && loads) {
+      const double* rec = A.rec + (int64_t)(i + 1) * VS_SREC;
 #pragma unroll
-        for (int r = 0; r < 9; r++) { c2[r] = L[r * 9 + gl]; if (gl == 2) c3[r] = L[r * 9 + 8]; }
-      } else {
-        const double* U = A.rec + (int64_t)left * VS_SREC + 81;
-#pragma unroll
-        for (int r = 0; r < 9; r++) { c2[r] = U[gl * 9 + r]; if (gl == 2) c3[r] = U[8 * 9 + r]; }
-      }
+      for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
     }
-  }
-  double v0[9], v2[9], v3[9];
+    // lower block Lo_i staged as M[k*kMS + r] = Lo_i[r][k]
+    if (A.lrec) {
+      const double* L = A.lrec + (int64_t)i * 81;
+      for (int idx = lane; idx < 81; idx += 32) { const int r = idx / 9, k = idx % 9; M[k * kMS + r] = L[idx]; }
+    } else if (isU) {
 #pragma unroll
-  for (int r = 0; r < 9; r++) { v0[r] = v2[r] = v3[r] = 0.0; }
-  bool first = true;
-  double w8[9];
-#pragma unroll
-  for (int r = 0; r < 9; r++) w8[r] = 0.0;
-
-  for (int t = 0; t < maxlen; t++) {
-    const int i = a + t;
-    const bool on = t < len;
-    if (on) {
-      // assemble the augmented columns of element i
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        c0[r] = n0[r] + (r == gl ? lam32 : 0.0) - v0[r];
-        c1[r] = n1[r];
-        if (!first) c2[r] = -v2[r];
-        double x = n3[r];
-        if (gl == 0) x = n3[r] + (r == 8 ? lam32 : 0.0) - v3[r];
-        else if (gl == 2) x = first ? c3[r] : -v3[r];
-        else if (gl == 3) x = n3[r] - v3[r];
-        c3[r] = x;
-      }
-      first = false;
-      if (t + 1 < len) load_cols(i + 1, n0, n1, n3);
-      // lower block Lo_i (for the update of element i+1), staged as M[k*9+r] = Lo_i[r][k]
-      if (A.lrec) {
-        const double* L = A.lrec + (int64_t)i * 81;
-        for (int idx = gl; idx < 81; idx += kGL) { const int r = idx / 9, k = idx % 9; M[k * 9 + r] = L[idx]; }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 9; r++) { M[r * 9 + gl] = c1[r]; if (gl == 1) M[r * 9 + 8] = c3[r]; }
-      }
+      for (int r = 0; r < 9; r++) M[r * kMS + cc] = a_[r];       // M[k][r'] = U[k][r'] = Lo[r'][k]
     }
     // Gauss-Jordan on [S | U | b | Z]
 #pragma unroll
     for (int k = 0; k < 9; k++) {
-      double pk[9];
+      if (c == k) {
 #pragma unroll
-      for (int r = 0; r < 9; r++) pk[r] = gshfl(k < 8 ? c0[r] : c3[r], k < 8 ? k : 0);
-      if (on) {
-        const double inv = fast_rcp_c(pk[k]);
-        const double p0 = c0[k] * inv, p1 = c1[k] * inv, p2 = c2[k] * inv, p3 = c3[k] * inv;
-#pragma unroll
-        for (int r = 0; r < 9; r++) {
-          if (r == k) { c0[r] = p0; c1[r] = p1; c2[r] = p2; c3[r] = p3; }
-          else {
-            c0[r] = fma(-pk[r], p0, c0[r]);
-            c1[r] = fma(-pk[r], p1, c1[r]);
-            if (SPIKE) c2[r] = fma(-pk[r], p2, c2[r]);
-            c3[r] = fma(-pk[r], p3, c3[r]);
-          }
-        }
+        for (int r = 0; r < 9; r++) colk[k & 1][r] = a_[r];
       }
-    }
-    // W_8 lives in lane 1; the S_8 update (lane 0) needs it
+      __syncwarp();
+      double pk[9];
+      {
+        const double2* p2 = reinterpret_cast<const double2*>(colk[k & 1]);
 #pragma unroll
-    for (int r = 0; r < 9; r++) w8[r] = gshfl(c3[r], 1);
-    __syncwarp();      // M complete
-    if (on) {
-      double* w = A.wrec + (int64_t)i * VS_WREC;
+        for (int r2 = 0; r2 < 4; r2++) { const double2 v = p2[r2]; pk[2 * r2] = v.x; pk[2 * r2 + 1] = v.y; }
+        pk[8] = colk[k & 1][8];
+      }
+      const double pr = a_[k] * fast_rcp_c(pk[k]);
 #pragma unroll
       for (int r = 0; r < 9; r++) {
-        w[gl * 9 + r] = c1[r];
-        if (SPIKE) w[90 + gl * 9 + r] = c2[r];
-        if (gl == 1) w[8 * 9 + r] = c3[r];
-        else if (gl == 2) { if (SPIKE) w[90 + 8 * 9 + r] = c3[r]; }
-        else if (gl == 3) w[81 + r] = c3[r];
-      }
-      // products with Lo_i: for element i+1, or (segment mode, last interior) for the separator's row
-      if (t + 1 < len || SPIKE) {
-        matvec9(M, c1, v0);
-        if (SPIKE) matvec9(M, c2, v2);
-        if (has_x && gl != 1) matvec9(M, gl == 0 ? w8 : c3, v3);
+        if (r == k) a_[r] = pr;
+        else a_[r] = fma(-pk[r], pr, a_[r]);
       }
     }
-    __syncwarp();      // before M is overwritten
+    // publish W (lanes 9..17) and y (lane 18) for the S / b lanes; store W, y, Z
+    if (isU || isB) {
+#pragma unroll
+      for (int r = 0; r < 9; r++) Ws[(c - 9) * 9 + r] = a_[r];
+    }
+    {
+      double* w = A.wrec + (int64_t)i * VS_WREC;
+      if (isU || isB) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) w[(c - 9) * 9 + r] = a_[r];
+      } else if (isZ) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) w[90 + cc * 9 + r] = a_[r];
+      }
+    }
+    __syncwarp();
+    // corr = Lo_i x (W_c | y | Z_c): for element i+1, and (segment mode) for the separator's row after the loop
+    if (i + 1 < e || SPIKE) {
+      if (isS || isB || isZ) {
+        double v[9];
+        if (isZ) {
+#pragma unroll
+          for (int k = 0; k < 9; k++) v[k] = a_[k];
+        } else {
+          const double* wc = Ws + (isS ? c : 9) * 9;
+#pragma unroll
+          for (int k = 0; k < 9; k++) v[k] = wc[k];
+        }
+        matvec9(M, v, corr);
+      }
+    }
+    __syncwarp();
   }
 
-  if (!SPIKE) {
-    // ---- plain mode: own backward substitution x_i = y_i - W_i x_{i+1}; lane l computes rows l (and 8) ----
-    double x[9];
+  if (SPIKE) {
+    // left part of the separator's row: Dl = -Lo W, bl = -Lo y, Ll = -Lo Z (all from the last interior element)
 #pragma unroll
-    for (int r = 0; r < 9; r++) x[r] = 0.0;
-    for (int t = maxlen - 1; t >= 0; t--) {
-      const bool on = t < len;
-      const int i = a + t;
-      double xa = 0.0, xb = 0.0;
-      if (on) {
-        const double* w = A.wrec + (int64_t)i * VS_WREC;
-        xa = w[81 + gl];
-        xb = w[81 + 8];
-        if (t + 1 < len) {
-#pragma unroll
-          for (int c = 0; c < 9; c++) { xa = fma(-w[c * 9 + gl], x[c], xa); xb = fma(-w[c * 9 + 8], x[c], xb); }
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 8; c++) { const double v = gshfl(xa, c); if (on) x[c] = v; }
-      if (on) {
-        x[8] = xb;
-        const int64_t row = A.out_index ? A.out_index[i] : i;
-        A.delta[row * 9 + gl] = xa;
-        if (gl == 0) A.delta[row * 9 + 8] = xb;
-      }
+    for (int r = 0; r < 9; r++) {
+      if (isS) rr[r * 9 + c] = -corr[r];
+      else if (isZ) rr[81 + r * 9 + cc] = -corr[r];
+      else if (isB) rr[162 + r] = -corr[r];
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// plain chains: backward substitution x_i = y_i - W_i x_{i+1}; lane r < 9 owns row r, records prefetched
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_chain_backward(ChainArgs A) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * 4 + warp;
+  if (ch >= A.n_chains) return;
+  if (A.active && !A.active[A.ch_prob[ch]]) return;
+  const int a = A.ch_a[ch], e = A.ch_b[ch];
+  if (e <= a) return;
+  const int lr = lane < 9 ? lane : 0;
+  double dn[9], wcur[10], wnx[10];
+#pragma unroll
+  for (int k = 0; k < 9; k++) dn[k] = 0.0;
+  {
+    const double* w = A.wrec + (int64_t)(e - 1) * VS_WREC;
+#pragma unroll
+    for (int k = 0; k < 9; k++) wnx[k] = w[k * 9 + lr];
+    wnx[9] = w[81 + lr];
+  }
+  for (int i = e - 1; i >= a; i--) {
+#pragma unroll
+    for (int k = 0; k < 10; k++) wcur[k] = wnx[k];
+    if (i > a) {
+      const double* w = A.wrec + (int64_t)(i - 1) * VS_WREC;
+#pragma unroll
+      for (int k = 0; k < 9; k++) wnx[k] = w[k * 9 + lr];
+      wnx[9] = w[81 + lr];
+    }
+    double dr = wcur[9];
+    if (i + 1 < e) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) dr = fma(-wcur[k], dn[k], dr);
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) dn[k] = __shfl_sync(0xffffffffu, dr, k);
+    const int64_t row = A.out_index ? A.out_index[i] : i;
+    if (lane < 9) A.delta[row * 9 + lane] = dr;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// segment mode, second pass: closed form x_a = yh - Wh x_b - Zh x_left by the backward recurrence
+//   Wh_i = -W_i Wh_{i+1},  Zh_i = Z_i - W_i Zh_{i+1},  yh_i = y_i - W_i yh_{i+1}   (started at the last interior)
+// and the RIGHT part of the left separator's row: Dr = -U_left Zh_a, Ur = -U_left Wh_a, br = -U_left yh_a.
+// Lanes 0-8 own Wh columns, lane 9 owns yh, lanes 10-18 own Zh columns.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_seg_backrec(ChainArgs A) {
+  __shared__ __align__(16) double s_M[4][9 * kMS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * 4 + warp;
+  if (ch >= A.n_chains) return;
+  if (A.active && !A.active[A.ch_prob[ch]]) return;
+  const int a = A.ch_a[ch], e = A.ch_b[ch], left = A.ch_left[ch];
+  double* rq = A.redrec + (int64_t)ch * VS_RREC + 171;
+  if (left < 0) {
+    for (int idx = lane; idx < 171; idx += 32) rq[idx] = 0.0;
     return;
   }
-
-  // ---- segment mode: contributions to the reduced system --------------------------------------------------
-  double* rr = valid ? A.redrec + (int64_t)ch * VS_RREC : nullptr;
-  // left part (row of this segment's separator b): Dl = -Lo_{b-1} W_{b-1}, bl = -Lo_{b-1} y_{b-1},
-  // Ll = -Lo_{b-1} Z_{b-1}  (coefficient of x_left); empty interior: Ll = Lo_left, Dl = bl = 0.
-  if (live) {
-    if (len > 0) {
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        rr[r * 9 + gl] = -v0[r];                      // Dl[r][gl]
-        rr[81 + r * 9 + gl] = -v2[r];                 // Ll[r][gl]
-        if (gl == 0) rr[r * 9 + 8] = -v3[r];
-        else if (gl == 2) rr[81 + r * 9 + 8] = -v3[r];
-        else if (gl == 3) rr[162 + r] = -v3[r];
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        double l0 = 0.0, l8 = 0.0;
-        if (left >= 0) {
-          if (A.lrec) { l0 = A.lrec[(int64_t)left * 81 + r * 9 + gl]; l8 = A.lrec[(int64_t)left * 81 + r * 9 + 8]; }
-          else { l0 = A.rec[(int64_t)left * VS_SREC + 81 + gl * 9 + r]; l8 = A.rec[(int64_t)left * VS_SREC + 81 + 8 * 9 + r]; }
-        }
-        rr[r * 9 + gl] = 0.0;
-        rr[81 + r * 9 + gl] = l0;
-        if (gl == 0) rr[r * 9 + 8] = 0.0;
-        else if (gl == 2) rr[81 + r * 9 + 8] = l8;
-        else if (gl == 3) rr[162 + r] = 0.0;
-      }
-    }
+  const double* Ul = A.rec + (int64_t)left * VS_SREC + 81;
+  if (e <= a) {      // no interior: Ur = U_left, Dr = br = 0
+    for (int idx = lane; idx < 171; idx += 32) rq[idx] = (idx >= 81 && idx < 162) ? Ul[idx - 81] : 0.0;
+    return;
   }
-  // right part (row of the LEFT separator): closed form x_a = yh - Wh x_b - Zh x_left by the backward recurrence
-  //   Wh_i = -W_i Wh_{i+1}, Zh_i = Z_i - W_i Zh_{i+1}, yh_i = y_i - W_i yh_{i+1}, started at the last interior.
-  // h1 = Wh column gl, h2 = Zh column gl, h3 = extra (lane0: Wh_8, lane2: Zh_8, lane3: yh)
-  double h1[9], h2[9], h3[9];
+  double* M = s_M[warp];
+  const bool isW = lane < 9, isY = lane == 9, isZ = lane >= 10 && lane < 19;
+  const int cc = isW ? lane : (isZ ? lane - 10 : 0);
+  // own column of element i inside a wrec record: W col cc | y | Z col cc
+  const int off = isW ? cc * 9 : (isY ? 81 : 90 + cc * 9);
+  const bool act = lane < 19;
+  double h[9], own[9];
+  {
+    const double* w = A.wrec + (int64_t)(e - 1) * VS_WREC;
 #pragma unroll
-  for (int r = 0; r < 9; r++) { h1[r] = c1[r]; h2[r] = c2[r]; h3[r] = (gl == 0) ? w8[r] : c3[r]; }
-  const bool need_right = live && left >= 0;
-  // segments of different length: a group starts its recurrence when the common counter reaches its own end
-  for (int t = maxlen - 2; t >= 0; t--) {
-    const bool on = need_right && (t < len - 1);
-    const int i = a + t;
-    if (on) {
-      const double* w = A.wrec + (int64_t)i * VS_WREC;
-      for (int idx = gl; idx < 81; idx += kGL) Wst[idx] = w[idx];
-    }
+    for (int r = 0; r < 9; r++) h[r] = act ? w[off + r] : 0.0;
+  }
+  for (int i = e - 2; i >= a; i--) {
+    const double* w = A.wrec + (int64_t)i * VS_WREC;
+    // stage W_i: M[c*kMS + r] = W_i[r][c]  (stored col-major at w[c*9 + r])
+    for (int idx = lane; idx < 81; idx += 32) M[(idx / 9) * kMS + (idx % 9)] = w[idx];
+#pragma unroll
+    for (int r = 0; r < 9; r++) own[r] = (act && !isW) ? w[off + r] : 0.0;
     __syncwarp();
-    if (on) {
-      const double* w = A.wrec + (int64_t)i * VS_WREC;
-      double o1[9], o2[9], o3[9];
-      matvec9(Wst, h1, o1);
-      matvec9(Wst, h2, o2);
-      matvec9(Wst, h3, o3);
+    double o[9];
+    matvec9(M, h, o);
 #pragma unroll
-      for (int r = 0; r < 9; r++) {
-        h1[r] = -o1[r];
-        h2[r] = w[90 + gl * 9 + r] - o2[r];
-        double own = 0.0;
-        if (gl == 2) own = w[90 + 8 * 9 + r];
-        else if (gl == 3) own = w[81 + r];
-        h3[r] = own - o3[r];
-      }
-    }
+    for (int r = 0; r < 9; r++) h[r] = own[r] - o[r];
     __syncwarp();
   }
-  if (need_right) {
-    // stage U_left transposed: Wst[k*9+r] = U_left[r][k]   (explicit mode: U of the reduced chain is in rec too)
-    const double* U = A.rec + (int64_t)left * VS_SREC + 81;
-    for (int idx = gl; idx < 81; idx += kGL) { const int r = idx / 9, k = idx % 9; Wst[k * 9 + r] = U[idx]; }
-  }
+  // M[k*kMS + r] = U_left[r][k]
+  for (int idx = lane; idx < 81; idx += 32) { const int r = idx / 9, k = idx % 9; M[k * kMS + r] = Ul[idx]; }
   __syncwarp();
-  if (need_right) {
-    double* rq = rr + 171;
-    if (len > 0) {
-      double o1[9], o2[9], o3[9];
-      matvec9(Wst, h1, o1);      // U_left Wh  -> Ur = -(...)
-      matvec9(Wst, h2, o2);      // U_left Zh  -> Dr = -(...)
-      matvec9(Wst, h3, o3);
+  double o[9];
+  matvec9(M, h, o);
 #pragma unroll
-      for (int r = 0; r < 9; r++) {
-        rq[r * 9 + gl] = -o2[r];                       // Dr[r][gl]
-        rq[81 + r * 9 + gl] = -o1[r];                  // Ur[r][gl]
-        if (gl == 0) rq[81 + r * 9 + 8] = -o3[r];      // Ur col 8 (from Wh_8)
-        else if (gl == 2) rq[r * 9 + 8] = -o3[r];      // Dr col 8 (from Zh_8)
-        else if (gl == 3) rq[162 + r] = -o3[r];        // br
-      }
-    } else {
-      const double* U = A.rec + (int64_t)left * VS_SREC + 81;
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        rq[r * 9 + gl] = 0.0;
-        rq[81 + r * 9 + gl] = U[r * 9 + gl];
-        if (gl == 0) rq[81 + r * 9 + 8] = U[r * 9 + 8];
-        else if (gl == 2) rq[r * 9 + 8] = 0.0;
-        else if (gl == 3) rq[162 + r] = 0.0;
-      }
-    }
-  } else if (live) {
-    double* rq = rr + 171;
-    for (int idx = gl; idx < 171; idx += kGL) rq[idx] = 0.0;
+  for (int r = 0; r < 9; r++) {
+    if (isZ) rq[r * 9 + cc] = -o[r];            // Dr
+    else if (isW) rq[81 + r * 9 + cc] = -o[r];  // Ur
+    else if (isY) rq[162 + r] = -o[r];          // br
   }
 }
 
@@ -382,57 +368,48 @@ __global__ void __launch_bounds__(256) k_reduced_build(int n_seg, const int32_t*
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// interior back-substitution of a segment: x_i = y_i - W_i x_{i+1} - Z_i x_left, i = b-1 .. a
+// interior back-substitution of a segment: x_i = y_i - W_i x_{i+1} - Z_i x_left, i = b-1 .. a.
+// Lane r < 9 owns row r; the next record is prefetched while the current one is used.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_seg_backsub(int n_chains, const int32_t* __restrict__ ch_a,
-                                                    const int32_t* __restrict__ ch_b,
-                                                    const int32_t* __restrict__ ch_left,
-                                                    const int32_t* __restrict__ ch_prob,
-                                                    const int32_t* __restrict__ active,
-                                                    const double* __restrict__ wrec, double* __restrict__ delta) {
-  const int lane = threadIdx.x & 31;
-  const int g = lane / kGL, gl = lane % kGL;
-  const int ch = blockIdx.x * kCPW + g;
-  int a = 0, b = 0, left = -1;
-  bool live = false;
-  if (ch < n_chains) {
-    a = ch_a[ch]; b = ch_b[ch]; left = ch_left[ch];
-    live = active ? (active[ch_prob[ch]] != 0) : true;
-  }
-  if (!live) { a = 0; b = 0; }
-  const int len = b - a;
-  int maxlen = len;
-#pragma unroll
-  for (int o = 16; o >= kGL; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-  double x[9], xl[9];
+__global__ void __launch_bounds__(128) k_seg_backsub(int n_chains, const int32_t* __restrict__ ch_a,
+                                                     const int32_t* __restrict__ ch_b,
+                                                     const int32_t* __restrict__ ch_left,
+                                                     const int32_t* __restrict__ ch_prob,
+                                                     const int32_t* __restrict__ active,
+                                                     const double* __restrict__ wrec, double* __restrict__ delta) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * 4 + warp;
+  if (ch >= n_chains) return;
+  if (active && !active[ch_prob[ch]]) return;
+  const int a = ch_a[ch], b = ch_b[ch], left = ch_left[ch];
+  if (b <= a) return;
+  const int lr = lane < 9 ? lane : 0;
+  double x[9], xl[9], cur[19], nx[19];
 #pragma unroll
   for (int r = 0; r < 9; r++) {
-    x[r] = live ? delta[(int64_t)b * 9 + r] : 0.0;
-    xl[r] = (live && left >= 0) ? delta[(int64_t)left * 9 + r] : 0.0;
+    x[r] = delta[(int64_t)b * 9 + r];
+    xl[r] = left >= 0 ? delta[(int64_t)left * 9 + r] : 0.0;
   }
-  for (int t = maxlen - 1; t >= 0; t--) {
-    const bool on = t < len;
-    const int i = a + t;
-    double xa = 0.0, xb = 0.0;
-    if (on) {
-      const double* w = wrec + (int64_t)i * VS_WREC;
-      xa = w[81 + gl];
-      xb = w[81 + 8];
+  auto fetch = [&](int i, double* d) {
+    const double* w = wrec + (int64_t)i * VS_WREC;
 #pragma unroll
-      for (int c = 0; c < 9; c++) {
-        xa = fma(-w[c * 9 + gl], x[c], xa);
-        xb = fma(-w[c * 9 + 8], x[c], xb);
-        xa = fma(-w[90 + c * 9 + gl], xl[c], xa);
-        xb = fma(-w[90 + c * 9 + 8], xl[c], xb);
-      }
-    }
+    for (int k = 0; k < 9; k++) { d[k] = w[k * 9 + lr]; d[10 + k] = w[90 + k * 9 + lr]; }
+    d[9] = w[81 + lr];
+  };
+  fetch(b - 1, nx);
+  for (int i = b - 1; i >= a; i--) {
 #pragma unroll
-    for (int c = 0; c < 8; c++) { const double v = gshfl(xa, c); if (on) x[c] = v; }
-    if (on) {
-      x[8] = xb;
-      delta[(int64_t)i * 9 + gl] = xa;
-      if (gl == 0) delta[(int64_t)i * 9 + 8] = xb;
-    }
+    for (int k = 0; k < 19; k++) cur[k] = nx[k];
+    if (i > a) fetch(i - 1, nx);
+    double zr = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) zr = fma(cur[10 + k], xl[k], zr);     // off the critical path
+    double dr = cur[9] - zr;
+#pragma unroll
+    for (int k = 0; k < 9; k++) dr = fma(-cur[k], x[k], dr);
+#pragma unroll
+    for (int k = 0; k < 9; k++) x[k] = __shfl_sync(0xffffffffu, dr, k);
+    if (lane < 9) delta[(int64_t)i * 9 + lane] = dr;
   }
 }
 
@@ -452,12 +429,14 @@ int launch_chain_solve(vinsat_batch* b) {
   if (!b->partitioned) {
     A.n_chains = (int)b->P;
     A.ch_a = b->pl_a; A.ch_b = b->pl_b; A.ch_left = nullptr; A.ch_prob = b->pl_prob;
-    VS_LAUNCH(ctx, F_SOLVE, k_chain<false>, ceil_div(A.n_chains, kCPW), 32, 0, A);
+    VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<false>, ceil_div(A.n_chains, kFwdWarps), kFwdWarps * 32, 0, A);
+    VS_LAUNCH(ctx, F_SOLVE, k_chain_backward, ceil_div(A.n_chains, 4), 128, 0, A);
     return VINSAT_OK;
   }
   A.n_chains = (int)b->n_seg;
   A.ch_a = b->seg_a; A.ch_b = b->seg_b; A.ch_left = b->seg_left; A.ch_prob = b->seg_prob;
-  VS_LAUNCH(ctx, F_SOLVE, k_chain<true>, ceil_div(A.n_chains, kCPW), 32, 0, A);
+  VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<true>, ceil_div(A.n_chains, kFwdWarps), kFwdWarps * 32, 0, A);
+  VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
   VS_LAUNCH(ctx, F_SOLVE, k_reduced_build, ceil_div((int64_t)b->n_seg * 192, 256), 256, 0, (int)b->n_seg, b->seg_b,
             b->seg_left, b->seg_prob, b->seg_has_next, b->active, b->lam, b->srec, b->redrec, b->rsys, b->rlow);
   ChainArgs R;
@@ -472,8 +451,9 @@ int launch_chain_solve(vinsat_batch* b) {
   R.delta = b->delta;
   R.out_index = b->seg_b;          // separator s -> frame b_s
   R.lam32_last = nullptr;
-  VS_LAUNCH(ctx, F_SOLVE, k_chain<false>, ceil_div(R.n_chains, kCPW), 32, 0, R);
-  VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div((int64_t)b->n_seg, kCPW), 32, 0, (int)b->n_seg, b->seg_a, b->seg_b,
+  VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<false>, ceil_div(R.n_chains, kFwdWarps), kFwdWarps * 32, 0, R);
+  VS_LAUNCH(ctx, F_SOLVE, k_chain_backward, ceil_div(R.n_chains, 4), 128, 0, R);
+  VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div((int64_t)b->n_seg, 4), 128, 0, (int)b->n_seg, b->seg_a, b->seg_b,
             b->seg_left, b->seg_prob, b->active, b->wrec, b->delta);
   return VINSAT_OK;
 }
