@@ -153,6 +153,34 @@ int vinsat_ctx_get_timing(vinsat_ctx* ctx, int cap, const char** names_out, doub
 /* Total kernel launches issued by this context since creation (bench.py's `gpu_launches`). */
 int64_t vinsat_ctx_launch_count(const vinsat_ctx* ctx);
 
+/* ---- frame-window sharded long arc (config 3) ----------------------------------------------
+ * One problem split by contiguous frame windows across ranks (one process per GPU).  The rank's batch holds
+ * its owned frames [own_lo, own_hi) plus at most one GHOST frame per side (the neighbour's edge frame: state,
+ * intrinsics, cum_rot, time) and the observations of the owned frames only.  The host drives the iteration
+ * stage by stage and exchanges the exposed device buffers between stages with NCCL (vinsat_b200/longarc.py
+ * documents the choreography).  Math and results are those of vinsat_batch_ba_iterate on the whole arc. */
+int vinsat_batch_create_window(vinsat_ctx* ctx, const vinsat_problem_desc* desc, int64_t own_lo, int64_t own_hi,
+                               int64_t n_segments, vinsat_batch** out);
+int vinsat_la_num_segments(const vinsat_batch* b);
+int vinsat_la_alloc_reduced(vinsat_batch* b, int64_t S_total, int64_t n_ranks);
+enum {
+  VINSAT_LA_RESID = 0, VINSAT_LA_SELECT_BEGIN, VINSAT_LA_SELECT_HIST, VINSAT_LA_SELECT_PICK, VINSAT_LA_ASSEMBLE,
+  VINSAT_LA_DYNAMICS, VINSAT_LA_SYSTEM, VINSAT_LA_SUMS_INIT, VINSAT_LA_SET_LAM, VINSAT_LA_SOLVE_INIT,
+  VINSAT_LA_FORWARD, VINSAT_LA_REDUCED, VINSAT_LA_BACKSUB, VINSAT_LA_RETRACT, VINSAT_LA_PACK_EDGES,
+  VINSAT_LA_APPLY_GHOSTS, VINSAT_LA_TRIAL, VINSAT_LA_SUMS_TRIAL, VINSAT_LA_COMMIT
+};
+enum {
+  VINSAT_LA_BUF_HIST = 0,   /* uint32[2048]   all-reduce SUM between SELECT_HIST and SELECT_PICK */
+  VINSAT_LA_BUF_WMAX,       /* int64[1]       all-reduce MAX after ASSEMBLE (bit pattern of a double >= 0) */
+  VINSAT_LA_BUF_SUMS,       /* float64[4]     all-reduce SUM after SUMS_INIT / SUMS_TRIAL */
+  VINSAT_LA_BUF_PACK,       /* float64[n_seg*514]  all-gather into GATHER after FORWARD */
+  VINSAT_LA_BUF_GATHER,     /* float64[S_total*514] */
+  VINSAT_LA_BUF_EDGE,       /* float64[20]    all-gather into EDGES_ALL after PACK_EDGES */
+  VINSAT_LA_BUF_EDGES_ALL   /* float64[n_ranks*20] */
+};
+int vinsat_la_stage(vinsat_batch* b, int stage, int64_t i0, int64_t i1, double d0);
+int vinsat_la_ptr(vinsat_batch* b, int which, void** ptr, int64_t* count);
+
 /* ---- a10: SatCam batched projection / visibility (sim/SatCam.py:87-92,125-154,175-262) -------------
  * poses [P,12] = [ECEF pos (m), dir, up, right] (SatCam.py:23-28; note up is negated, :52,81);
  * landmarks_ecef [L,3] (m).  uv_out [P,L,2] nullable; inframe_out [P,L] uint8 nullable

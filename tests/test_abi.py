@@ -25,7 +25,7 @@ def test_library_built_and_loads():
 
 def test_every_header_symbol_is_exported_and_bound():
     syms = header_symbols()
-    assert len(syms) >= 31
+    assert len(syms) >= 36
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for s in syms:
         assert hasattr(raw, s), "missing export: " + s

@@ -1,0 +1,67 @@
+"""Frame-window sharded long arc (configs[2]): the staged, exchange-driven solve must equal the ordinary
+batched solve of the whole arc.  Multi-rank runs are emulated with several windows in one process on one GPU
+(same stages, same buffers; reductions done by the test driver instead of NCCL); the real NCCL path is
+exercised by tests/run_longarc_nccl.py under torchrun."""
+import numpy as np
+import pytest
+
+import ba_oracle as o
+from vinsat_b200 import _lib, longarc, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def _whole(ctx, pr, iters):
+    b = _lib.Batch(ctx, _lib.concat_problems([pr]))
+    lam = np.array([1e-4]); hist = []
+    for it, init in iters:
+        lam, ntr = b.ba_iterate(it, lam, initialize=init)
+        hist.append((b.get_states().copy(), float(lam[0]), int(ntr[0])))
+    b.close()
+    return hist
+
+
+@pytest.mark.parametrize("world,nseg", [(1, 1), (1, 4), (2, 1), (2, 3), (3, 2), (4, 5)])
+def test_sharded_iterations_equal_whole_arc(ctx, world, nseg):
+    pr = synth.make_problem(77, 120, 6)
+    iters = [(0, True), (1, True), (9, True), (10, False), (11, False), (14, False), (19, False)]
+    ref = _whole(ctx, pr, iters)
+    la = longarc.LongArc(pr, ctxs=[ctx], world=world, n_segments=nseg)
+    lam = 1e-4
+    for k, (it, init) in enumerate(iters):
+        lam, ntr = la.ba_iterate(it, lam, initialize=init)
+        st = la.gather_states()
+        s_ref, lam_ref, ntr_ref = ref[k]
+        assert ntr == ntr_ref and lam == lam_ref, (world, nseg, it)
+        assert np.abs(st[:, :3] - s_ref[:, :3]).max() < 1e-6, (world, nseg, it)      # 1 mm
+        assert np.abs(st[:, 7:] - s_ref[:, 7:]).max() < 1e-9, (world, nseg, it)
+        assert np.abs(st[:, 3:7] - s_ref[:, 3:7]).max() < 1e-10, (world, nseg, it)
+    assert la.n_collectives > 0
+    la.close()
+
+
+def test_sharded_od_solve_converges_like_oracle(ctx):
+    pr = synth.make_problem(78, 90, 5)
+    la = longarc.LongArc(pr, ctxs=[ctx], world=3, n_segments=2)
+    la.od_solve(20, 10, 1e-4)
+    st = la.gather_states()
+    ref, _, _ = o.od_solve(pr["states0"].copy(), pr["cum_rot"], pr["uv"], pr["xyz"], pr["ii"], pr["time_idx"], pr["intr"], pr["conf"])
+    assert np.abs(st[:, :3] - ref[:, :3]).max() < 1e-3 and np.abs(st[:, 7:] - ref[:, 7:]).max() < 1e-6
+    la.close()
+
+
+def test_window_plan():
+    assert longarc.plan_windows(10, 3) == [(0, 3), (3, 6), (6, 10)]
+    pr = synth.make_problem(1, 12, 2)
+    a, lo, hi = longarc.window_arrays(pr, 4, 8)
+    assert a["frame_off"][1] == 6 and (lo, hi) == (1, 5)                    # one ghost each side
+    assert a["obs_off"][1] == 8 and a["ii"].min() == 1 and a["ii"].max() == 4
+    a, lo, hi = longarc.window_arrays(pr, 0, 4)
+    assert a["frame_off"][1] == 5 and (lo, hi) == (0, 4)

@@ -51,6 +51,12 @@ SIGNATURES = {
     "vinsat_orbit_propagate": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double,
                                          C.c_void_p, C.c_void_p]),
     "vinsat_batch_create": (C.c_int, [C.c_void_p, C.POINTER(ProblemDesc), C.POINTER(C.c_void_p)]),
+    "vinsat_batch_create_window": (C.c_int, [C.c_void_p, C.POINTER(ProblemDesc), C.c_int64, C.c_int64, C.c_int64,
+                                             C.POINTER(C.c_void_p)]),
+    "vinsat_la_num_segments": (C.c_int, [C.c_void_p]),
+    "vinsat_la_alloc_reduced": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
+    "vinsat_la_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_double]),
+    "vinsat_la_ptr": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "vinsat_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(ProblemDesc)]),
     "vinsat_batch_set_states": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "vinsat_batch_get_states": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
@@ -268,8 +274,9 @@ def concat_problems(problems):
 class Batch:
     """Device-resident batch of independent OD problems (``vinsat_batch``)."""
 
-    def __init__(self, ctx, arrays):
-        """arrays: dict as returned by concat_problems (NumPy or pinned torch tensors; kept alive here)."""
+    def __init__(self, ctx, arrays, window=None):
+        """arrays: dict as returned by concat_problems (NumPy or pinned torch tensors; kept alive here).
+        window=(own_lo, own_hi, n_segments): frame-window of a sharded long arc (vinsat_b200/longarc.py)."""
         self.ctx = ctx
         self.lib = ctx.lib
         self.P = len(arrays["frame_off"]) - 1
@@ -279,7 +286,11 @@ class Batch:
         self.M = int(self.obs_off[-1])
         self._desc = self._make_desc(arrays)
         h = C.c_void_p()
-        ctx.check(self.lib.vinsat_batch_create(ctx.h, C.byref(self._desc), C.byref(h)))
+        if window is None:
+            ctx.check(self.lib.vinsat_batch_create(ctx.h, C.byref(self._desc), C.byref(h)))
+        else:
+            ctx.check(self.lib.vinsat_batch_create_window(ctx.h, C.byref(self._desc), int(window[0]), int(window[1]),
+                                                          int(window[2]), C.byref(h)))
         self.h = h
 
     def _make_desc(self, a):

@@ -34,7 +34,8 @@ void free_all(vinsat_batch* b) {
                   b->d_frame_off, b->d_obs_off, b->c_obs, b->wmax, b->lam, b->lam_next, b->lam32_last, b->init_res,
                   b->active, b->ntrials, b->sel_prefix, b->sel_rank, b->sel_hist, b->flags, b->seg_a, b->seg_b,
                   b->seg_left, b->seg_prob, b->seg_has_next, b->pl_a, b->pl_b, b->pl_prob, b->red_a, b->red_b,
-                  b->redrec, b->rsys, b->rlow, b->rwrec};
+                  b->redrec, b->rsys, b->rlow, b->rwrec, b->la_pack, b->la_gath, b->la_rsys, b->la_rlow, b->la_rwrec,
+                  b->la_xsep, b->la_sums, b->la_edge, b->la_edges_all, b->la_chain};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (b->h_flags) cudaFreeHost(b->h_flags);
@@ -100,8 +101,26 @@ struct Segmentation {
   bool partitioned = false;
 };
 
-Segmentation make_segments(const vinsat_ctx* ctx, int64_t P, const int64_t* frame_off) {
+Segmentation make_segments(const vinsat_ctx* ctx, int64_t P, const int64_t* frame_off, const vinsat_batch* wb = nullptr) {
   Segmentation s;
+  if (wb && wb->window) {
+    // frame-window sharded arc: segments over the OWNED frames only; the left ghost (if any) is the left separator
+    const int64_t lo = wb->own_lo, hi = wb->own_hi, Tp = hi - lo;
+    const int64_t S = std::max<int64_t>(1, std::min<int64_t>(wb->forced_segments, Tp));
+    s.pl_a.push_back(0); s.pl_b.push_back((int32_t)frame_off[1]); s.pl_prob.push_back(0);
+    s.red_a.push_back(0);
+    for (int64_t k = 0; k < S; k++) {
+      const int64_t a = lo + (Tp * k) / S, b = lo + (Tp * (k + 1)) / S;
+      s.a.push_back((int32_t)a);
+      s.b.push_back((int32_t)(b - 1));
+      s.left.push_back(a > 0 ? (int32_t)(a - 1) : -1);
+      s.prob.push_back(0);
+      s.has_next.push_back(k + 1 < S ? 1 : 0);
+    }
+    s.red_b.push_back((int32_t)S);
+    s.partitioned = true;
+    return s;
+  }
   const int64_t T = frame_off[P];
   int64_t forced = 0;
   if (const char* e = getenv("VINSAT_SEG_LEN")) forced = atoll(e);
@@ -160,7 +179,7 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
   VS_CUDA(ctx, cudaMemcpyAsync(b->intr, d->intrinsics, T * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
   VS_CUDA(ctx, cudaMemcpyAsync(b->crot, d->cum_rot, T * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
   {
-    Segmentation sg = make_segments(ctx, P, d->frame_off);
+    Segmentation sg = make_segments(ctx, P, d->frame_off, b);
     if ((int64_t)sg.a.size() != b->n_seg)
       return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_upload: segmentation differs (frame_off must not change)");
     b->partitioned = sg.partitioned;
@@ -204,24 +223,37 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
 
 extern "C" {
 
-int vinsat_batch_create(vinsat_ctx* ctx, const vinsat_problem_desc* d, vinsat_batch** out) {
+static int create_impl(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t own_lo, int64_t own_hi, int64_t n_segments,
+                       vinsat_batch** out) {
   if (!ctx || !out) return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_create: NULL argument");
   *out = nullptr;
   VS_TRY(validate_desc(ctx, d));
   VS_CUDA(ctx, cudaSetDevice(ctx->device));
   vinsat_batch* b = new vinsat_batch();
   b->ctx = ctx;
+  if (n_segments > 0) {
+    if (d->n_problems != 1 || own_lo < 0 || own_hi <= own_lo || own_hi > d->frame_off[1] || own_lo > 1 ||
+        own_hi < d->frame_off[1] - 1) {
+      delete b;
+      return set_error(ctx, VINSAT_EINVAL, "window: one problem, owned range plus at most one ghost frame per side");
+    }
+    b->window = true;
+    b->own_lo = own_lo;
+    b->own_hi = own_hi;
+    b->forced_segments = n_segments;
+  }
   b->P = d->n_problems;
   b->T = d->frame_off[b->P];
   b->M = d->obs_off[b->P];
   const int64_t P = b->P, T = b->T, M = b->M;
-  b->n_seg = (int64_t)make_segments(ctx, P, d->frame_off).a.size();
+  b->n_seg = (int64_t)make_segments(ctx, P, d->frame_off, b).a.size();
   const int64_t NS = b->n_seg;
   int rc = VINSAT_OK;
 #define A(ptr, n) if (rc == VINSAT_OK) rc = dev_alloc(ctx, &b->ptr, (n))
   A(seg_a, NS); A(seg_b, NS); A(seg_left, NS); A(seg_prob, NS); A(seg_has_next, NS);
   A(pl_a, P); A(pl_b, P); A(pl_prob, P); A(red_a, P); A(red_b, P);
   A(redrec, NS * VS_RREC); A(rsys, NS * VS_SREC); A(rlow, NS * 81); A(rwrec, NS * VS_WREC);
+  if (b->window) { A(la_pack, NS * (VS_RREC + VS_SREC)); A(la_sums, 4); A(la_edge, 20); }
   A(st, T * 10); A(st_new, T * 10); A(intr, T * 4); A(crot, T * 4); A(gap, T); A(fprob, T); A(dyn_order, T);
   A(obs_start, T + 1); A(grec, T * VS_GREC); A(drec, T * VS_DREC); A(srec, T * VS_SREC); A(wrec, T * VS_WREC);
   A(delta, T * 9); A(e_obs, T); A(e_dyn, T);
@@ -247,6 +279,16 @@ int vinsat_batch_create(vinsat_ctx* ctx, const vinsat_problem_desc* d, vinsat_ba
   }
   *out = b;
   return VINSAT_OK;
+}
+
+int vinsat_batch_create(vinsat_ctx* ctx, const vinsat_problem_desc* d, vinsat_batch** out) {
+  return create_impl(ctx, d, 0, 0, 0, out);
+}
+
+int vinsat_batch_create_window(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t own_lo, int64_t own_hi,
+                               int64_t n_segments, vinsat_batch** out) {
+  if (n_segments < 1) return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_create_window: n_segments must be >= 1");
+  return create_impl(ctx, d, own_lo, own_hi, n_segments, out);
 }
 
 int vinsat_batch_upload(vinsat_batch* b, const vinsat_problem_desc* d) {

@@ -66,6 +66,21 @@ struct vinsat_batch {
   unsigned int* sel_hist = nullptr;          // [P][2048]
   int32_t* flags = nullptr;    // [4]: 0 = n_active, 1 = index error
   int32_t* h_flags = nullptr;  // pinned mirror
+  // ---- frame-window sharded long arc (longarc.cu): this batch holds ONE problem = owned frames + ghosts ----
+  bool window = false;
+  int64_t own_lo = 0, own_hi = 0;     // owned local frames [own_lo, own_hi); ghosts (if any) at own_lo-1 / own_hi
+  int64_t forced_segments = 0;
+  int64_t S_total = 0, n_ranks = 0;
+  double* la_pack = nullptr;          // [n_seg][VS_RREC + VS_SREC]
+  double* la_gath = nullptr;          // [S_total][VS_RREC + VS_SREC]
+  double* la_rsys = nullptr;          // [S_total][VS_SREC]
+  double* la_rlow = nullptr;          // [S_total][81]
+  double* la_rwrec = nullptr;         // [S_total][VS_WREC]
+  double* la_xsep = nullptr;          // [S_total][9]
+  double* la_sums = nullptr;          // [4]
+  double* la_edge = nullptr;          // [2][10] new states of the first / last owned frame
+  double* la_edges_all = nullptr;     // [n_ranks][2][10]
+  int32_t* la_chain = nullptr;        // {0, S_total, 0}
   bool have_iter = false;
   bool srec_valid = false;
   double last_sigma = 0.0;

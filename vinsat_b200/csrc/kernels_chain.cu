@@ -413,6 +413,88 @@ __global__ void __launch_bounds__(128) k_seg_backsub(int n_chains, const int32_t
   }
 }
 
+// reduced system of a frame-window sharded arc from the all-gathered per-segment packs
+//   pack[s] = { redrec (VS_RREC) | system record of the separator frame (VS_SREC) }, one problem, global order
+__global__ void __launch_bounds__(256) k_reduced_build_packed(int n_seg, const double* __restrict__ pack,
+                                                              const double* __restrict__ lam,
+                                                              double* __restrict__ rsys, double* __restrict__ rlow) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int s = (int)(t / 192);
+  const int e = (int)(t % 192);
+  if (s >= n_seg || e >= 171) return;
+  constexpr int kPack = VS_RREC + VS_SREC;
+  const double* mine = pack + (int64_t)s * kPack;
+  const double* fr = mine + VS_RREC;
+  const bool nx = s + 1 < n_seg;
+  const double* next = pack + (int64_t)(s + 1) * kPack + 171;
+  double v;
+  if (e < 81) {
+    v = fr[e] + mine[e] + (nx ? next[e] : 0.0);
+    if (e / 9 == e % 9) v += (double)(float)lam[0];
+  } else if (e < 162) {
+    v = nx ? next[e] : 0.0;
+  } else {
+    v = fr[e] + mine[e] + (nx ? next[e] : 0.0);
+  }
+  rsys[(int64_t)s * VS_SREC + e] = v;
+  if (e < 81 && s > 0) rlow[(int64_t)(s - 1) * 81 + e] = mine[81 + e];
+}
+
+static ChainArgs seg_args(vinsat_batch* b) {
+  ChainArgs A;
+  A.active = b->active;
+  A.lam = b->lam;
+  A.rec = b->srec;
+  A.lrec = nullptr;
+  A.wrec = b->wrec;
+  A.delta = b->delta;
+  A.out_index = nullptr;
+  A.lam32_last = b->lam32_last;
+  A.redrec = b->redrec;
+  A.n_chains = (int)b->n_seg;
+  A.ch_a = b->seg_a; A.ch_b = b->seg_b; A.ch_left = b->seg_left; A.ch_prob = b->seg_prob;
+  return A;
+}
+
+int launch_seg_forward(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->n_seg == 0) return VINSAT_OK;
+  ChainArgs A = seg_args(b);
+  VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<true>, ceil_div(A.n_chains, kFwdWarps), kFwdWarps * 32, 0, A);
+  VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
+  return VINSAT_OK;
+}
+
+int launch_seg_backsub(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->n_seg == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div((int64_t)b->n_seg, 4), 128, 0, (int)b->n_seg, b->seg_a, b->seg_b,
+            b->seg_left, b->seg_prob, b->active, b->wrec, b->delta);
+  return VINSAT_OK;
+}
+
+int launch_reduced_packed(vinsat_batch* b, int64_t S_total, const double* pack, double* rsys, double* rlow,
+                          double* rwrec, double* xsep, const int32_t* one_chain) {
+  vinsat_ctx* ctx = b->ctx;
+  VS_LAUNCH(ctx, F_SOLVE, k_reduced_build_packed, ceil_div(S_total * 192, 256), 256, 0, (int)S_total, pack, b->lam, rsys,
+            rlow);
+  ChainArgs R;
+  R.n_chains = 1;
+  R.ch_a = one_chain; R.ch_b = one_chain + 1; R.ch_left = nullptr; R.ch_prob = one_chain + 2;
+  R.active = nullptr;
+  R.lam = nullptr;
+  R.rec = rsys;
+  R.lrec = rlow;
+  R.wrec = rwrec;
+  R.redrec = nullptr;
+  R.delta = xsep;
+  R.out_index = nullptr;
+  R.lam32_last = nullptr;
+  VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<false>, 1, kFwdWarps * 32, 0, R);
+  VS_LAUNCH(ctx, F_SOLVE, k_chain_backward, 1, 128, 0, R);
+  return VINSAT_OK;
+}
+
 int launch_chain_solve(vinsat_batch* b) {
   vinsat_ctx* ctx = b->ctx;
   if (b->P == 0 || b->T == 0) return VINSAT_OK;

@@ -86,25 +86,54 @@ __global__ void __launch_bounds__(256) k_select_pick(unsigned long long* __restr
   if (last && threadIdx.x == 0 && obs_off[p + 1] == obs_off[p]) c_obs[p] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
-int launch_select_median(vinsat_batch* b) {
+static const int kSelShift[6] = {53, 42, 31, 20, 9, 0};
+static const int kSelBits[6] = {11, 11, 11, 11, 11, 9};
+
+__global__ void k_select_set_rank(unsigned long long* __restrict__ prefix, unsigned long long* __restrict__ rank,
+                                  unsigned long long r) {
+  prefix[0] = 0ull;
+  rank[0] = r;
+}
+
+int launch_select_begin(vinsat_batch* b, int64_t global_values) {
   vinsat_ctx* ctx = b->ctx;
-  if (b->P == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_SELECT, k_select_init, ceil_div(b->P, 128), 128, 0, (int)b->P, b->d_obs_off, b->sel_prefix,
-            b->sel_rank);
-  const int shifts[6] = {53, 42, 31, 20, 9, 0};
-  const int nbits[6] = {11, 11, 11, 11, 11, 9};
+  if (global_values < 0) {
+    VS_LAUNCH(ctx, F_SELECT, k_select_init, ceil_div(b->P, 128), 128, 0, (int)b->P, b->d_obs_off, b->sel_prefix,
+              b->sel_rank);
+  } else {   // frame-window sharded single problem: the rank counts every rank's values
+    VS_LAUNCH(ctx, F_SELECT, k_select_set_rank, 1, 1, 0, b->sel_prefix, b->sel_rank,
+              (unsigned long long)(global_values > 0 ? (global_values - 1) / 2 : 0));
+  }
+  return VINSAT_OK;
+}
+
+int launch_select_hist(vinsat_batch* b, int pass) {
+  vinsat_ctx* ctx = b->ctx;
   int64_t chunks = ceil_div(2 * b->max_obs_per_problem, 256 * 16);
   if (chunks < 1) chunks = 1;
   const int64_t cap = std::max<int64_t>(1, (int64_t)ctx->sm_count * 8 / std::max<int64_t>(1, b->P));
   if (chunks > cap) chunks = cap;
-  for (int pass = 0; pass < 6; pass++) {
-    dim3 grid((unsigned)chunks, (unsigned)b->P);
-    VS_LAUNCH(ctx, F_SELECT, k_select_hist, grid, 256, 0, b->M, b->d_obs_off, b->r, b->sel_prefix, shifts[pass],
-              nbits[pass], b->sel_hist);
-    VS_LAUNCH(ctx, F_SELECT, k_select_pick, (unsigned)b->P, 256, 0, b->sel_prefix, b->sel_rank, shifts[pass],
-              b->sel_hist, pass == 5 ? 1 : 0, b->c_obs, b->d_obs_off);
-  }
+  dim3 grid((unsigned)chunks, (unsigned)b->P);
+  VS_LAUNCH(ctx, F_SELECT, k_select_hist, grid, 256, 0, b->M, b->d_obs_off, b->r, b->sel_prefix, kSelShift[pass],
+            kSelBits[pass], b->sel_hist);
   return VINSAT_OK;
+}
+
+int launch_select_pick(vinsat_batch* b, int pass) {
+  vinsat_ctx* ctx = b->ctx;
+  VS_LAUNCH(ctx, F_SELECT, k_select_pick, (unsigned)b->P, 256, 0, b->sel_prefix, b->sel_rank, kSelShift[pass],
+            b->sel_hist, pass == 5 ? 1 : 0, b->c_obs, b->d_obs_off);
+  return VINSAT_OK;
+}
+
+int launch_select_median(vinsat_batch* b) {
+  if (b->P == 0) return VINSAT_OK;
+  int rc = launch_select_begin(b, -1);
+  for (int pass = 0; pass < 6 && rc == VINSAT_OK; pass++) {
+    rc = launch_select_hist(b, pass);
+    if (rc == VINSAT_OK) rc = launch_select_pick(b, pass);
+  }
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -381,6 +410,22 @@ __global__ void __launch_bounds__(128) k_retract(int64_t T, const int32_t* __res
   const Quat n = qmul(q, qexp(d[3], d[4], d[5]));
   const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z + n.w * n.w);
   o[3] = n.x / nn; o[4] = n.y / nn; o[5] = n.z / nn; o[6] = n.w / nn;
+}
+
+int launch_solve_init_only(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->T == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_SOLVE_INIT, k_solve_init, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->lam, b->wmax,
+            b->grec, b->delta, b->lam32_last);
+  return VINSAT_OK;
+}
+
+int launch_retract_only(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  if (b->T == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_RETRACT, k_retract, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->st, b->delta,
+            b->st_new);
+  return VINSAT_OK;
 }
 
 int launch_solve_retract(vinsat_batch* b, int initialize) {

@@ -40,13 +40,23 @@ int launch_orbit_propagate(vinsat_ctx* ctx, int64_t n_traj, int64_t n_steps, int
 
 // ---- kernels_solve.cu -------------------------------------------------------------------------------
 int launch_select_median(vinsat_batch* b);                       // c_obs[p] = lower median of |r|
+int launch_select_begin(vinsat_batch* b, int64_t global_values);  // -1: per-problem counts; else global count (long arc)
+int launch_select_hist(vinsat_batch* b, int pass);               // histogram of digit `pass` into sel_hist
+int launch_select_pick(vinsat_batch* b, int pass);               // narrow the prefix from sel_hist (and zero it)
 int launch_system_build(vinsat_batch* b, int initialize, double Sigma, double vel_coeff);
 int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double lamda_host_default,
                          const double* d_lam_in);
 int launch_solve_retract(vinsat_batch* b, int initialize);
+int launch_solve_init_only(vinsat_batch* b);
+int launch_retract_only(vinsat_batch* b);
 int launch_accept(vinsat_batch* b, int initialize, double Sigma);
 
 // ---- kernels_chain.cu -------------------------------------------------------------------------------
 int launch_chain_solve(vinsat_batch* b);   // delta = A^-1 rhs for every active problem (partitioned block LU)
+// pieces of the partitioned solve, for the frame-window sharded long arc (longarc.cu)
+int launch_seg_forward(vinsat_batch* b);                                    // segments: forward + back-recurrence -> redrec
+int launch_seg_backsub(vinsat_batch* b);                                    // interiors from separator solutions in delta
+int launch_reduced_packed(vinsat_batch* b, int64_t S_total, const double* pack, double* rsys, double* rlow,
+                          double* rwrec, double* xsep, const int32_t* one_chain /* {0, S_total, 0} on device */);
 
 }  // namespace vs
