@@ -17,6 +17,8 @@
 // 84 KB of SASS and was instruction-fetch bound).  Gauss-Jordan without pivoting (the symmetric part of every
 // pivot block is positive definite); the pivot column is broadcast through shared memory.
 // Parallelism comes from the number of chains (P x segments), ~35 resident warps per SM at P = 1024.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -76,7 +78,7 @@ constexpr int kFwdWarps = 4;
 // ---------------------------------------------------------------------------------------------------------
 template <bool SPIKE>
 __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
-  __shared__ __align__(16) double s_col[kFwdWarps][2][kMS];
+  __shared__ __align__(16) double s_col[kFwdWarps][2][3][kMS];
   __shared__ __align__(16) double s_M[kFwdWarps][9 * kMS];
   __shared__ __align__(16) double s_W[kFwdWarps][10 * 9];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
   const int base = isS ? c : (isU ? 81 + (c - 9) : 162);
   const int rstride = isB ? 1 : 9;
   const bool loads = isS || isU || isB;
-  double (*colk)[kMS] = s_col[warp];
+  double (*colk3)[3][kMS] = s_col[warp];
   double* M = s_M[warp];
   double* Ws = s_W[warp];
   double* rr = SPIKE ? A.redrec + (int64_t)ch * VS_RREC : nullptr;
@@ -161,26 +163,44 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
 #pragma unroll
       for (int r = 0; r < 9; r++) M[r * kMS + cc] = a_[r];       // M[k][r'] = U[k][r'] = Lo[r'][k]
     }
-    // Gauss-Jordan on [S | U | b | Z]
+    // Block Gauss-Jordan on [S | U | b | Z] with 3x3 pivot blocks (position, rotation, velocity): three dependent
+    // pivot steps per element instead of nine.  The three pivot columns are broadcast through shared memory,
+    // every lane inverts the 3x3 pivot block in closed form (adjugate, one reciprocal) and updates its column.
 #pragma unroll
-    for (int k = 0; k < 9; k++) {
-      if (c == k) {
+    for (int kb = 0; kb < 3; kb++) {
+      if (c >= 3 * kb && c < 3 * kb + 3) {
+        double* dst = colk3[kb & 1][c - 3 * kb];
 #pragma unroll
-        for (int r = 0; r < 9; r++) colk[k & 1][r] = a_[r];
+        for (int r = 0; r < 9; r++) dst[r] = a_[r];
       }
       __syncwarp();
-      double pk[9];
-      {
-        const double2* p2 = reinterpret_cast<const double2*>(colk[k & 1]);
+      double pc[3][9];
 #pragma unroll
-        for (int r2 = 0; r2 < 4; r2++) { const double2 v = p2[r2]; pk[2 * r2] = v.x; pk[2 * r2 + 1] = v.y; }
-        pk[8] = colk[k & 1][8];
+      for (int j = 0; j < 3; j++) {
+        const double2* p2 = reinterpret_cast<const double2*>(colk3[kb & 1][j]);
+#pragma unroll
+        for (int r2 = 0; r2 < 4; r2++) { const double2 v = p2[r2]; pc[j][2 * r2] = v.x; pc[j][2 * r2 + 1] = v.y; }
+        pc[j][8] = colk3[kb & 1][j][8];
       }
-      const double pr = a_[k] * fast_rcp_c(pk[k]);
+      const int o = 3 * kb;
+      const double p00 = pc[0][o], p10 = pc[0][o + 1], p20 = pc[0][o + 2];
+      const double p01 = pc[1][o], p11 = pc[1][o + 1], p21 = pc[1][o + 2];
+      const double p02 = pc[2][o], p12 = pc[2][o + 1], p22 = pc[2][o + 2];
+      const double c00 = p11 * p22 - p12 * p21, c01 = p12 * p20 - p10 * p22, c02 = p10 * p21 - p11 * p20;
+      const double inv = fast_rcp_c(p00 * c00 + p01 * c01 + p02 * c02);
+      const double i00 = c00 * inv, i01 = (p02 * p21 - p01 * p22) * inv, i02 = (p01 * p12 - p02 * p11) * inv;
+      const double i10 = c01 * inv, i11 = (p00 * p22 - p02 * p20) * inv, i12 = (p02 * p10 - p00 * p12) * inv;
+      const double i20 = c02 * inv, i21 = (p01 * p20 - p00 * p21) * inv, i22 = (p00 * p11 - p01 * p10) * inv;
+      const double b0 = a_[o], b1 = a_[o + 1], b2 = a_[o + 2];
+      const double t0 = i00 * b0 + i01 * b1 + i02 * b2;
+      const double t1 = i10 * b0 + i11 * b1 + i12 * b2;
+      const double t2 = i20 * b0 + i21 * b1 + i22 * b2;
 #pragma unroll
       for (int r = 0; r < 9; r++) {
-        if (r == k) a_[r] = pr;
-        else a_[r] = fma(-pk[r], pr, a_[r]);
+        if (r == o) a_[r] = t0;
+        else if (r == o + 1) a_[r] = t1;
+        else if (r == o + 2) a_[r] = t2;
+        else a_[r] = fma(-pc[2][r], t2, fma(-pc[1][r], t1, fma(-pc[0][r], t0, a_[r])));
       }
     }
     // publish W (lanes 9..17) and y (lane 18) for the S / b lanes; store W, y, Z
@@ -229,43 +249,53 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// plain chains: backward substitution x_i = y_i - W_i x_{i+1}; lane r < 9 owns row r, records prefetched
+// plain chains: backward substitution x_i = y_i - W_i x_{i+1}; lane r < 9 owns row r.  The per-frame work is
+// ~150 cycles but a W record comes from HBM (~800 cycles), so records are streamed through a shared-memory ring
+// with cp.async, kRing frames ahead.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int kRing = 8;
+
 __global__ void __launch_bounds__(128) k_chain_backward(ChainArgs A) {
+  __shared__ __align__(16) double s_ring[4][kRing][96];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x * 4 + warp;
   if (ch >= A.n_chains) return;
   if (A.active && !A.active[A.ch_prob[ch]]) return;
   const int a = A.ch_a[ch], e = A.ch_b[ch];
   if (e <= a) return;
-  const int lr = lane < 9 ? lane : 0;
-  double dn[9], wcur[10], wnx[10];
+  double (*ring)[96] = s_ring[warp];
+  auto issue = [&](int i, int slot) {          // W (81) | y (9) of element i -> ring[slot][0..90)
+    if (i >= a) {
+      const double* w = A.wrec + (int64_t)i * VS_WREC;
+      for (int idx = lane; idx < 90; idx += 32) __pipeline_memcpy_async(&ring[slot][idx], w + idx, 8);
+    }
+    __pipeline_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < kRing; d++) issue(e - 1 - d, d);
+  double dn[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) dn[k] = 0.0;
-  {
-    const double* w = A.wrec + (int64_t)(e - 1) * VS_WREC;
-#pragma unroll
-    for (int k = 0; k < 9; k++) wnx[k] = w[k * 9 + lr];
-    wnx[9] = w[81 + lr];
-  }
+  int slot = 0;
   for (int i = e - 1; i >= a; i--) {
+    __pipeline_wait_prior(kRing - 1);
+    __syncwarp();
+    double dr = 0.0;
+    if (lane < 9) {
+      const double* w = ring[slot];
+      dr = w[81 + lane];
+      if (i + 1 < e) {
 #pragma unroll
-    for (int k = 0; k < 10; k++) wcur[k] = wnx[k];
-    if (i > a) {
-      const double* w = A.wrec + (int64_t)(i - 1) * VS_WREC;
-#pragma unroll
-      for (int k = 0; k < 9; k++) wnx[k] = w[k * 9 + lr];
-      wnx[9] = w[81 + lr];
+        for (int k = 0; k < 9; k++) dr = fma(-w[k * 9 + lane], dn[k], dr);
+      }
     }
-    double dr = wcur[9];
-    if (i + 1 < e) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) dr = fma(-wcur[k], dn[k], dr);
-    }
+    __syncwarp();
+    issue(i - kRing, slot);
 #pragma unroll
     for (int k = 0; k < 9; k++) dn[k] = __shfl_sync(0xffffffffu, dr, k);
     const int64_t row = A.out_index ? A.out_index[i] : i;
     if (lane < 9) A.delta[row * 9 + lane] = dr;
+    slot = (slot + 1 == kRing) ? 0 : slot + 1;
   }
 }
 
@@ -369,7 +399,7 @@ __global__ void __launch_bounds__(256) k_reduced_build(int n_seg, const int32_t*
 
 // ---------------------------------------------------------------------------------------------------------
 // interior back-substitution of a segment: x_i = y_i - W_i x_{i+1} - Z_i x_left, i = b-1 .. a.
-// Lane r < 9 owns row r; the next record is prefetched while the current one is used.
+// Lane r < 9 owns row r; records are streamed through a cp.async ring like k_chain_backward.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_seg_backsub(int n_chains, const int32_t* __restrict__ ch_a,
                                                      const int32_t* __restrict__ ch_b,
@@ -377,39 +407,49 @@ __global__ void __launch_bounds__(128) k_seg_backsub(int n_chains, const int32_t
                                                      const int32_t* __restrict__ ch_prob,
                                                      const int32_t* __restrict__ active,
                                                      const double* __restrict__ wrec, double* __restrict__ delta) {
+  __shared__ __align__(16) double s_ring[4][kRing][176];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x * 4 + warp;
   if (ch >= n_chains) return;
   if (active && !active[ch_prob[ch]]) return;
   const int a = ch_a[ch], b = ch_b[ch], left = ch_left[ch];
   if (b <= a) return;
-  const int lr = lane < 9 ? lane : 0;
-  double x[9], xl[9], cur[19], nx[19];
+  double (*ring)[176] = s_ring[warp];
+  auto issue = [&](int i, int slot) {
+    if (i >= a) {
+      const double* w = wrec + (int64_t)i * VS_WREC;
+      for (int idx = lane; idx < 171; idx += 32) __pipeline_memcpy_async(&ring[slot][idx], w + idx, 8);
+    }
+    __pipeline_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < kRing; d++) issue(b - 1 - d, d);
+  double x[9], xl[9];
 #pragma unroll
   for (int r = 0; r < 9; r++) {
     x[r] = delta[(int64_t)b * 9 + r];
     xl[r] = left >= 0 ? delta[(int64_t)left * 9 + r] : 0.0;
   }
-  auto fetch = [&](int i, double* d) {
-    const double* w = wrec + (int64_t)i * VS_WREC;
-#pragma unroll
-    for (int k = 0; k < 9; k++) { d[k] = w[k * 9 + lr]; d[10 + k] = w[90 + k * 9 + lr]; }
-    d[9] = w[81 + lr];
-  };
-  fetch(b - 1, nx);
+  int slot = 0;
   for (int i = b - 1; i >= a; i--) {
+    __pipeline_wait_prior(kRing - 1);
+    __syncwarp();
+    double dr = 0.0;
+    if (lane < 9) {
+      const double* w = ring[slot];
+      double zr = 0.0;
 #pragma unroll
-    for (int k = 0; k < 19; k++) cur[k] = nx[k];
-    if (i > a) fetch(i - 1, nx);
-    double zr = 0.0;
+      for (int k = 0; k < 9; k++) zr = fma(w[90 + k * 9 + lane], xl[k], zr);     // off the critical path
+      dr = w[81 + lane] - zr;
 #pragma unroll
-    for (int k = 0; k < 9; k++) zr = fma(cur[10 + k], xl[k], zr);     // off the critical path
-    double dr = cur[9] - zr;
-#pragma unroll
-    for (int k = 0; k < 9; k++) dr = fma(-cur[k], x[k], dr);
+      for (int k = 0; k < 9; k++) dr = fma(-w[k * 9 + lane], x[k], dr);
+    }
+    __syncwarp();
+    issue(i - kRing, slot);
 #pragma unroll
     for (int k = 0; k < 9; k++) x[k] = __shfl_sync(0xffffffffu, dr, k);
     if (lane < 9) delta[(int64_t)i * 9 + lane] = dr;
+    slot = (slot + 1 == kRing) ? 0 : slot + 1;
   }
 }
 
