@@ -30,7 +30,7 @@ int dev_alloc(vinsat_ctx* ctx, T** p, int64_t n) {
 
 void free_all(vinsat_batch* b) {
   void* ptrs[] = {b->st, b->st_new, b->intr, b->crot, b->gap, b->fprob, b->dyn_order, b->obs_start, b->grec, b->drec,
-                  b->srec, b->wrec, b->delta, b->e_obs, b->e_dyn, b->X, b->uv, b->conf, b->oframe, b->r, b->wu, b->J,
+                  b->srec, b->wrec, b->delta, b->e_obs, b->e_dyn, b->X, b->uv, b->conf, b->oframe, b->r, b->r_next, b->wu, b->J,
                   b->d_frame_off, b->d_obs_off, b->c_obs, b->wmax, b->lam, b->lam_next, b->lam32_last, b->init_res,
                   b->active, b->ntrials, b->sel_prefix, b->sel_rank, b->sel_hist, b->flags, b->seg_a, b->seg_b,
                   b->seg_left, b->seg_prob, b->seg_has_next, b->pl_a, b->pl_b, b->pl_prob, b->red_a, b->red_b,
@@ -216,6 +216,7 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
   if (b->h_flags[1] & 1) return set_error(ctx, VINSAT_EINVAL, "ii out of range for its problem's frame count");
   if (b->h_flags[1] & 2) return set_error(ctx, VINSAT_EINVAL, "ii must be non-decreasing inside each problem");
   b->have_iter = false;
+  b->r_valid = false;
   return VINSAT_OK;
 }
 
@@ -257,7 +258,7 @@ static int create_impl(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t ow
   A(st, T * 10); A(st_new, T * 10); A(intr, T * 4); A(crot, T * 4); A(gap, T); A(fprob, T); A(dyn_order, T);
   A(obs_start, T + 1); A(grec, T * VS_GREC); A(drec, T * VS_DREC); A(srec, T * VS_SREC); A(wrec, T * VS_WREC);
   A(delta, T * 9); A(e_obs, T); A(e_dyn, T);
-  A(X, M * 3); A(uv, M * 2); A(conf, M); A(oframe, M); A(r, M * 2); A(wu, M);
+  A(X, M * 3); A(uv, M * 2); A(conf, M); A(oframe, M); A(r, M * 2); A(r_next, M * 2); A(wu, M);
   A(d_frame_off, P + 1); A(d_obs_off, P + 1); A(c_obs, P); A(wmax, P); A(lam, P); A(lam_next, P); A(lam32_last, P);
   A(init_res, P); A(active, P); A(ntrials, P); A(sel_prefix, P); A(sel_rank, P); A(sel_hist, P * 2048); A(flags, 4);
 #undef A
@@ -314,6 +315,7 @@ int vinsat_batch_set_states(vinsat_batch* b, int mem, const double* states) {
                                mem == VINSAT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                ctx->stream));
   if (mem != VINSAT_MEM_DEVICE) VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  b->r_valid = false;
   return VINSAT_OK;
 }
 
@@ -335,7 +337,10 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
   const double alpha = std::min(std::max(1.0 - (2.0 * ((double)iter / 5.0) - 1.0), 1.0), 2.0);   // :22
   const double it1 = (double)iter + 1.0;
   const double Sigma = std::min(10000.0 * it1 * it1, 1000000.0);                       // :26
-  VS_TRY(launch_obs_residual(b));
+  // the last LM trial of the previous call already evaluated uv - project(states) at the returned states
+  // (bit-identical arithmetic), so its residuals are reused instead of projecting every observation again
+  if (b->r_valid) std::swap(b->r, b->r_next);
+  else VS_TRY(launch_obs_residual(b));
   VS_TRY(launch_select_median(b));
   VS_TRY(launch_obs_assemble(b, alpha));
   if (!initialize) {
@@ -361,6 +366,7 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
     if (b->h_flags[0] == 0) break;
   }
   std::swap(b->st, b->st_new);     // every problem's last trial is returned, accepted or not (:60,98)
+  b->r_valid = true;
   b->have_iter = true;
   b->last_initialize = initialize;
   return VINSAT_OK;

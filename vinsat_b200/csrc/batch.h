@@ -48,6 +48,8 @@ struct vinsat_batch {
   double* conf = nullptr;      // [M]
   int32_t* oframe = nullptr;   // [M] global frame of the observation
   double* r = nullptr;         // [2][M] residuals
+  double* r_next = nullptr;    // [2][M] residuals at the last trial's states = next iteration's residuals
+  bool r_valid = false;
   double* wu = nullptr;        // [M] conf * w_raw (un-normalised robust weight)
   double* J = nullptr;         // [12][M] headline kernel output (allocated on first use)
   // ---- device, per problem ----

@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const i
                                                    const int32_t* __restrict__ active, const double* __restrict__ X,
                                                    const double* __restrict__ uv, const double* __restrict__ wu,
                                                    const double* __restrict__ st, const double* __restrict__ intr,
-                                                   double* __restrict__ e_obs) {
+                                                   double* __restrict__ e_obs, double* __restrict__ r_next) {
   const int gl = threadIdx.x & (kGroup - 1);
   const int64_t f = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kGroup;
   const bool valid = f < T;
@@ -669,7 +669,10 @@ __global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const i
       for (int k = k0 + gl; k < k1; k += kGroup) {
         ProjOut o = project_exact(s[0], s[1], s[2], q, X[k], X[M + k], X[2 * M + k], ci.x, ci.y, ci.z, ci.w);
         const double w = wu[k];
-        e += fabs(xsub(uv[k], o.u) * w) + fabs(xsub(uv[M + k], o.v) * w);
+        const double ru = xsub(uv[k], o.u), rv = xsub(uv[M + k], o.v);
+        r_next[k] = ru;
+        r_next[M + k] = rv;
+        e += fabs(ru * w) + fabs(rv * w);
       }
     }
   }
@@ -682,10 +685,10 @@ int launch_obs_trial(vinsat_batch* b) {
   if (b->T == 0) return VINSAT_OK;
   if (b->M <= 16 * b->T) {
     VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<4>, ceil_div(b->T * 4, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
-              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs);
+              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
   } else {
     VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<8>, ceil_div(b->T * 8, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
-              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs);
+              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
   }
   return VINSAT_OK;
 }

@@ -221,11 +221,140 @@ __global__ void __launch_bounds__(256) k_system(int64_t T, const int32_t* __rest
   if (lane == 0) out[171] = 0.0;
 }
 
+// Second version: 3 threads per frame (row blocks pos / rot / vel), 32 frames per CTA.  The frames' observation
+// and dynamics records are staged with coalesced loads into shared memory; every thread then builds three
+// complete rows of D, U and b in registers and writes them as contiguous runs (~20 warp-instructions per frame
+// instead of ~600 for the element-per-lane version above, which is kept for reference / testing).
+constexpr int kSysFrames = 32;
+constexpr int kSysStride = VS_GREC + VS_DREC + 7;     // 99 doubles: odd stride => conflict-free row access
+constexpr int kSysOut = VS_SREC + 1;                  // 173: odd stride of the staged output records
+
+__global__ void __launch_bounds__(96) k_system_rows(int64_t T, const int32_t* __restrict__ gap,
+                                                    const int32_t* __restrict__ fprob,
+                                                    const unsigned long long* __restrict__ wmax,
+                                                    const double* __restrict__ grec, const double* __restrict__ drec,
+                                                    int initialize, double Sigma, double vc,
+                                                    double* __restrict__ srec) {
+  extern __shared__ __align__(16) double sys_smem[];
+  double* sm = sys_smem;                                   // [kSysFrames][kSysStride] inputs
+  double* so = sys_smem + kSysFrames * kSysStride;         // [kSysFrames][kSysOut]    outputs
+  const int tid = threadIdx.x;
+  const int64_t f0 = (int64_t)blockIdx.x * kSysFrames;
+  const int nf = (int)min((int64_t)kSysFrames, T - f0);
+  for (int i = tid; i < nf * VS_GREC; i += 96) sm[(i / VS_GREC) * kSysStride + (i % VS_GREC)] = grec[f0 * VS_GREC + i];
+  if (!initialize) {
+    for (int i = tid; i < nf * VS_DREC; i += 96)
+      sm[(i / VS_DREC) * kSysStride + VS_GREC + (i % VS_DREC)] = drec[f0 * VS_DREC + i];
+    if (tid < 6) sm[VS_GREC + VS_DREC + tid] = (f0 > 0) ? drec[(f0 - 1) * VS_DREC + 36 + tid] : 0.0;   // r of the pair before the tile
+  }
+  __syncthreads();
+  const int lf = tid / 3, q = tid % 3;          // local frame, row block (0 pos, 1 rot, 2 vel)
+  if (lf < nf) {
+  const int64_t f = f0 + lf;
+  const double* G = sm + lf * kSysStride;
+  const double* Dr = G + VS_GREC;
+  const double* rp = (lf > 0) ? (G - kSysStride + VS_GREC + 36) : (sm + VS_GREC + VS_DREC);   // r6 of pair (f-1, f)
+  const bool has_next = !initialize && gap[f] > 0;
+  const bool has_prev = !initialize && f > 0 && gap[f - 1] > 0;
+  const unsigned long long wb = wmax[fprob[f]];
+  const double invw = wb ? 1.0 / __longlong_as_double((long long)wb) : 0.0;
+  const double dv2[6] = {1.0, 1.0, 1.0, vc * vc, vc * vc, vc * vc};
+  const double dv1[6] = {1.0, 1.0, 1.0, vc, vc, vc};
+  double* out = so + lf * kSysOut;
+  double Drow[3][9], Urow[3][9], brow[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    brow[i] = 0.0;
+#pragma unroll
+    for (int c = 0; c < 9; c++) { Drow[i][c] = 0.0; Urow[i][c] = 0.0; }
+  }
+  if (q == 1) {
+    // rotation rows 3..5: observation block columns 0..5, Sigma*Hq_diag / Sigma*Hq_off in the rotation columns
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const int a = 3 + i;
+#pragma unroll
+      for (int c = 0; c < 6; c++) Drow[i][c] = invw * G[a <= c ? sym_index(a, c) : sym_index(c, a)];
+      brow[i] = invw * G[21 + a];
+      if (!initialize) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          Drow[i][3 + c] += Sigma * Dr[46 + i * 3 + c];
+          if (has_next) Urow[i][3 + c] = Sigma * Dr[55 + i * 3 + c];
+        }
+        brow[i] -= Sigma * Dr[43 + i];
+      }
+    }
+  } else {
+    // position rows 0..2 (q = 0) or velocity rows 6..8 (q = 2): pv index pa = 3*(q/2) + i
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const int a = (q == 0) ? i : 6 + i;
+      const int pa = (q == 0) ? i : 3 + i;
+      if (q == 0) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) Drow[i][c] = invw * G[a <= c ? sym_index(a, c) : sym_index(c, a)];
+        brow[i] = invw * G[21 + a];
+      }
+      if (has_next) {
+        double col[6];      // dv2[k] * Phi[k][pa]
+#pragma unroll
+        for (int k = 0; k < 6; k++) col[k] = dv2[k] * Dr[k * 6 + pa];
+#pragma unroll
+        for (int pc = 0; pc < 6; pc++) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; k++) s = fma(col[k], Dr[k * 6 + pc], s);
+          Drow[i][pc < 3 ? pc : pc + 3] += Sigma * s;
+          Urow[i][pc < 3 ? pc : pc + 3] = -Sigma * Dr[pc * 6 + pa] * dv2[pc];
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s = fma(Dr[k * 6 + pa] * dv1[k], Dr[36 + k], s);
+        brow[i] -= Sigma * s;
+      }
+      if (has_prev) {
+        if (q == 0) Drow[i][i] += Sigma * dv2[i];
+        else Drow[i][6 + i] += Sigma * dv2[3 + i];
+        brow[i] += Sigma * dv1[pa] * rp[pa];
+      }
+    }
+  }
+  const int r0 = 3 * q;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+      out[(r0 + i) * 9 + c] = Drow[i][c];
+      out[81 + (r0 + i) * 9 + c] = Urow[i][c];
+    }
+    out[162 + r0 + i] = brow[i];
+  }
+  if (q == 0) out[171] = 0.0;
+  }
+  __syncthreads();
+  // coalesced write-out of the staged records
+  double* dst = srec + f0 * VS_SREC;
+  for (int i = tid; i < nf * VS_SREC; i += 96) dst[i] = so[(i / VS_SREC) * kSysOut + (i % VS_SREC)];
+}
+
 int launch_system_build(vinsat_batch* b, int initialize, double Sigma, double vel_coeff) {
   vinsat_ctx* ctx = b->ctx;
   if (b->T == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_SYSTEM, k_system, ceil_div(b->T, 8), 256, 0, b->T, b->gap, b->fprob, b->wmax, b->grec, b->drec,
-            initialize, Sigma, vel_coeff, b->srec);
+  static const bool legacy = getenv("VINSAT_SYSTEM_LEGACY") != nullptr;
+  if (legacy) {
+    VS_LAUNCH(ctx, F_SYSTEM, k_system, ceil_div(b->T, 8), 256, 0, b->T, b->gap, b->fprob, b->wmax, b->grec, b->drec,
+              initialize, Sigma, vel_coeff, b->srec);
+  } else {
+    const int smem = kSysFrames * (kSysStride + kSysOut) * (int)sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+      VS_CUDA(ctx, cudaFuncSetAttribute(k_system_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    VS_LAUNCH(ctx, F_SYSTEM, k_system_rows, ceil_div(b->T, kSysFrames), 96, smem, b->T, b->gap, b->fprob, b->wmax,
+              b->grec, b->drec, initialize, Sigma, vel_coeff, b->srec);
+  }
   return VINSAT_OK;
 }
 
