@@ -86,6 +86,72 @@ __global__ void __launch_bounds__(256) k_select_pick(unsigned long long* __restr
   if (last && threadIdx.x == 0 && obs_off[p + 1] == obs_off[p]) c_obs[p] = __longlong_as_double(0x7ff8000000000000LL);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Small problems (2 M_p keys fit in shared memory, e.g. 20 000 keys = 160 KB): ONE CTA per problem keeps the keys
+// resident and runs all six radix-select passes on chip: one pass over HBM instead of six plus 12 launches.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 1024;
+
+__global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const int64_t* __restrict__ obs_off,
+                                                             const double* __restrict__ r, double* __restrict__ c_obs) {
+  extern __shared__ __align__(16) unsigned long long sel_keys[];
+  __shared__ unsigned int hist[kSelBins];
+  __shared__ unsigned int wsum[32];
+  __shared__ unsigned long long s_prefix, s_rank;
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t k0 = obs_off[p], Mp = obs_off[p + 1] - k0;
+  const int n = (int)(2 * Mp);
+  if (n == 0) {
+    if (tid == 0) c_obs[p] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+  for (int i = tid; i < n; i += kSelThreads) {
+    const int comp = i >= Mp ? 1 : 0;
+    sel_keys[i] = (unsigned long long)__double_as_longlong(fabs(r[(int64_t)comp * M + k0 + (i - comp * Mp)]));
+  }
+  if (tid == 0) { s_prefix = 0ull; s_rank = (unsigned long long)((n - 1) / 2); }
+  const int shifts[6] = {53, 42, 31, 20, 9, 0};
+  const int nbits[6] = {11, 11, 11, 11, 11, 9};
+#pragma unroll 1
+  for (int pass = 0; pass < 6; pass++) {
+    for (int i = tid; i < kSelBins; i += kSelThreads) hist[i] = 0;
+    __syncthreads();
+    const unsigned long long pre = s_prefix;
+    const int shift = shifts[pass], hs = shift + nbits[pass];
+    const unsigned int dmask = (1u << nbits[pass]) - 1u;
+    for (int i = tid; i < n; i += kSelThreads) {
+      const unsigned long long key = sel_keys[i];
+      const bool match = hs >= 64 ? true : ((key >> hs) == (pre >> hs));
+      if (match) atomicAdd(&hist[(unsigned int)(key >> shift) & dmask], 1u);
+    }
+    __syncthreads();
+    // each thread owns bins 2*tid, 2*tid+1; block-wide exclusive scan of the pair sums
+    const unsigned int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
+    unsigned int s = h0 + h1, incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned int w = wsum[lane], wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+      wsum[lane] = wi - w;          // exclusive prefix of the warp sums
+    }
+    __syncthreads();
+    const unsigned long long before = (unsigned long long)wsum[warp] + (incl - s);
+    const unsigned long long rk = s_rank;
+    __syncthreads();
+    if (rk >= before && rk < before + s) {
+      const int bin = (rk < before + h0) ? 2 * tid : 2 * tid + 1;
+      s_prefix = pre | ((unsigned long long)bin << shift);
+      s_rank = rk - (bin == 2 * tid ? before : before + h0);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) c_obs[p] = __longlong_as_double((long long)s_prefix);
+}
+
 static const int kSelShift[6] = {53, 42, 31, 20, 9, 0};
 static const int kSelBits[6] = {11, 11, 11, 11, 11, 9};
 
@@ -128,6 +194,19 @@ int launch_select_pick(vinsat_batch* b, int pass) {
 
 int launch_select_median(vinsat_batch* b) {
   if (b->P == 0) return VINSAT_OK;
+  static const bool no_smem = getenv("VINSAT_SELECT_GLOBAL") != nullptr;
+  const int64_t keys = 2 * b->max_obs_per_problem;
+  if (!no_smem && keys > 0 && keys <= 26000 && !b->window) {
+    vinsat_ctx* ctx = b->ctx;
+    const int smem = (int)(keys * sizeof(unsigned long long));
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+      VS_CUDA(ctx, cudaFuncSetAttribute(k_select_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_smem = smem;
+    }
+    VS_LAUNCH(ctx, F_SELECT, k_select_smem, (unsigned)b->P, kSelThreads, smem, b->M, b->d_obs_off, b->r, b->c_obs);
+    return VINSAT_OK;
+  }
   int rc = launch_select_begin(b, -1);
   for (int pass = 0; pass < 6 && rc == VINSAT_OK; pass++) {
     rc = launch_select_hist(b, pass);
