@@ -29,7 +29,7 @@ int dev_alloc(vinsat_ctx* ctx, T** p, int64_t n) {
   } while (0)
 
 void free_all(vinsat_batch* b) {
-  void* ptrs[] = {b->st, b->st_new, b->intr, b->crot, b->gap, b->fprob, b->dyn_order, b->obs_start, b->grec, b->drec,
+  void* ptrs[] = {b->st, b->st_new, b->intr, b->crot, b->gap, b->fprob, b->dyn_order, b->obs_start, b->grec, b->drec, b->mrec,
                   b->srec, b->wrec, b->delta, b->e_obs, b->e_dyn, b->X, b->uv, b->conf, b->oframe, b->r, b->r_next, b->wu, b->J,
                   b->d_frame_off, b->d_obs_off, b->c_obs, b->wmax, b->lam, b->lam_next, b->lam32_last, b->init_res,
                   b->active, b->ntrials, b->sel_prefix, b->sel_rank, b->sel_hist, b->flags, b->seg_a, b->seg_b,
@@ -256,7 +256,7 @@ static int create_impl(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t ow
   A(redrec, NS * VS_RREC); A(rsys, NS * VS_SREC); A(rlow, NS * 81); A(rwrec, NS * VS_WREC);
   if (b->window) { A(la_pack, NS * (VS_RREC + VS_SREC)); A(la_sums, 4); A(la_edge, 20); }
   A(st, T * 10); A(st_new, T * 10); A(intr, T * 4); A(crot, T * 4); A(gap, T); A(fprob, T); A(dyn_order, T);
-  A(obs_start, T + 1); A(grec, T * VS_GREC); A(drec, T * VS_DREC); A(srec, T * VS_SREC); A(wrec, T * VS_WREC);
+  A(obs_start, T + 1); A(grec, T * VS_GREC); A(drec, T * VS_DREC); A(mrec, T * VS_MREC); A(srec, T * VS_SREC); A(wrec, T * VS_WREC);
   A(delta, T * 9); A(e_obs, T); A(e_dyn, T);
   A(X, M * 3); A(uv, M * 2); A(conf, M); A(oframe, M); A(r, M * 2); A(r_next, M * 2); A(wu, M);
   A(d_frame_off, P + 1); A(d_obs_off, P + 1); A(c_obs, P); A(wmax, P); A(lam, P); A(lam_next, P); A(lam32_last, P);
@@ -344,14 +344,17 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
   VS_TRY(launch_select_median(b));
   VS_TRY(launch_obs_assemble(b, alpha));
   if (!initialize) {
-    VS_TRY(launch_dynamics_stm(ctx, b->n_pairs, b->dyn_order, b->st, b->gap, vel_coeff, mode, b->drec, nullptr));
+    VS_TRY(launch_dynamics_stm(ctx, b->n_pairs, b->dyn_order, b->st, b->gap, vel_coeff, mode, b->drec, nullptr, b->mrec));
     VS_TRY(launch_quat_terms(ctx, b->T, b->st, b->crot, b->gap, quat_coeff, b->drec));
   }
   // initialize phase: block-diagonal system, solved straight from the observation records (k_solve_init);
   // the full records are only materialised on demand (last_hessian / debug_fetch).
+  // The plain (unpartitioned) sweep builds its columns on the fly from the per-frame records (fused system
+  // build); the partitioned sweep and the diagnostics read the materialised records.
   if (!initialize) VS_TRY(launch_system_build(b, 0, Sigma, vel_coeff));
   b->srec_valid = !initialize;
   b->last_sigma = Sigma;
+  b->cur_sigma = Sigma;
   VS_TRY(launch_init_residual(b, initialize, Sigma, 0.0, lam_dev_in));
   for (int trial = 0; trial < 16; trial++) {
     VS_TRY(launch_solve_retract(b, initialize));

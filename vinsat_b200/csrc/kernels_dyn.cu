@@ -17,12 +17,13 @@ namespace vs {
 __global__ void __launch_bounds__(128) k_dynamics_stm(int64_t n_pairs, const int32_t* __restrict__ order,
                                                       const double* __restrict__ st,
                                                       const int32_t* __restrict__ gap, double vel_coeff, int mode,
-                                                      double* __restrict__ drec, double* __restrict__ x_pred) {
+                                                      double* __restrict__ drec, double* __restrict__ x_pred,
+                                                      double* __restrict__ mrec) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t j = t >> 1;
   const int half = (int)(t & 1);
-  if (j >= n_pairs) return;
-  const int64_t f = order ? order[j] : j;
+  const bool live = (t >> 1) < n_pairs;
+  const int64_t j = live ? (t >> 1) : n_pairs - 1;      // dead tail threads shadow the last pair (no early exit:
+  const int64_t f = order ? order[j] : j;               // the lane pair exchanges its columns with shuffles below)
   const double* s = st + f * 10;
   double x[6] = {s[0], s[1], s[2], s[7], s[8], s[9]};
   double phi[3][6];
@@ -36,31 +37,77 @@ __global__ void __launch_bounds__(128) k_dynamics_stm(int64_t n_pairs, const int
   const int nh = num_hops(g, mode);
   for (int k = 0; k < nh; k++) rk4_step_stm<3>(x, phi, hop_size(g, mode, k));
   double* d = drec + f * VS_DREC;
+  if (live) {
 #pragma unroll
-  for (int c = 0; c < 3; c++)
+    for (int c = 0; c < 3; c++)
 #pragma unroll
-    for (int k = 0; k < 6; k++) d[k * 6 + half * 3 + c] = phi[c][k];
-  if (half == 0) {
+      for (int k = 0; k < 6; k++) d[k * 6 + half * 3 + c] = phi[c][k];
+  }
+  double r6[6] = {0, 0, 0, 0, 0, 0};
+  if (has_next) {
+    const double* sn = s + 10;
+    r6[0] = x[0] - sn[0]; r6[1] = x[1] - sn[1]; r6[2] = x[2] - sn[2];
+    r6[3] = (x[3] - sn[7]) * vel_coeff; r6[4] = (x[4] - sn[8]) * vel_coeff; r6[5] = (x[5] - sn[9]) * vel_coeff;
+  }
+  if (live && half == 0) {
     if (x_pred) {
 #pragma unroll
       for (int k = 0; k < 6; k++) x_pred[f * 6 + k] = x[k];
     }
-    if (has_next) {
-      const double* sn = s + 10;
-      d[36] = x[0] - sn[0]; d[37] = x[1] - sn[1]; d[38] = x[2] - sn[2];
-      d[39] = (x[3] - sn[7]) * vel_coeff; d[40] = (x[4] - sn[8]) * vel_coeff; d[41] = (x[5] - sn[9]) * vel_coeff;
-    } else {
 #pragma unroll
-      for (int k = 36; k < 42; k++) d[k] = 0.0;
+    for (int k = 0; k < 6; k++) d[36 + k] = r6[k];
+  }
+  if (mrec) {
+    // Phi^T D^2 Phi (upper triangle) and Phi^T D r for the normal equations: the partner's three columns come
+    // over with shuffles; this thread produces the entries whose FIRST column it owns.
+    double other[3][6];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int k = 0; k < 6; k++) other[c][k] = __shfl_xor_sync(0xffffffffu, phi[c][k], 1);
+    const double dv1[6] = {1.0, 1.0, 1.0, vel_coeff, vel_coeff, vel_coeff};
+    double* m = mrec + f * VS_MREC;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const int a = half * 3 + c;
+      double wcol[6];                                   // D^2 Phi[:, a]
+#pragma unroll
+      for (int k = 0; k < 6; k++) wcol[k] = dv1[k] * dv1[k] * phi[c][k];
+      // entries (a, b) with b >= a: own columns b = a .. 3*half+2, and (half 0 only) the partner's columns 3..5
+#pragma unroll
+      for (int c2 = 0; c2 < 3; c2++) {
+        if (c2 >= c) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; k++) sacc = fma(wcol[k], phi[c2][k], sacc);
+          const int bcol = half * 3 + c2;
+          if (live) m[a * 6 - (a * (a - 1)) / 2 + (bcol - a)] = sacc;
+        }
+      }
+      if (half == 0) {
+#pragma unroll
+        for (int c2 = 0; c2 < 3; c2++) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; k++) sacc = fma(wcol[k], other[c2][k], sacc);
+          const int bcol = 3 + c2;
+          if (live) m[a * 6 - (a * (a - 1)) / 2 + (bcol - a)] = sacc;
+        }
+      }
+      double vacc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) vacc = fma(phi[c][k] * dv1[k], r6[k], vacc);
+      if (live) m[21 + a] = vacc;
     }
+    if (live && half == 1) m[27] = 0.0;
   }
 }
 
 int launch_dynamics_stm(vinsat_ctx* ctx, int64_t n_pairs, const int32_t* order, const double* st,
-                        const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred) {
+                        const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred, double* mrec) {
   if (n_pairs == 0) return VINSAT_OK;
   VS_LAUNCH(ctx, F_DYNAMICS, k_dynamics_stm, ceil_div(n_pairs * 2, 128), 128, 0, n_pairs, order, st, gap, vel_coeff,
-            mode, drec, x_pred);
+            mode, drec, x_pred, mrec);
   return VINSAT_OK;
 }
 

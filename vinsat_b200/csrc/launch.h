@@ -25,7 +25,7 @@ int launch_soa_to_aos(vinsat_ctx* ctx, const double* soa, double* aos, int64_t n
 // ---- kernels_dyn.cu ---------------------------------------------------------------------------------
 // RK4 + STM for the pairs listed in `order` (2 threads per pair): writes Phi, r6 into drec; x_pred optional.
 int launch_dynamics_stm(vinsat_ctx* ctx, int64_t n_pairs, const int32_t* order, const double* st,
-                        const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred);
+                        const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred, double* mrec);
 // Quaternion smoothness terms per frame: rho, qgrad, Hq_diag, Hq_off into drec.
 int launch_quat_terms(vinsat_ctx* ctx, int64_t T, const double* st, const double* crot, const int32_t* gap,
                       double quat_coeff, double* drec);

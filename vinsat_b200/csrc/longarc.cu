@@ -160,7 +160,7 @@ int vinsat_la_stage(vinsat_batch* b, int stage, int64_t i0, int64_t i1, double d
     case VINSAT_LA_SELECT_PICK: return launch_select_pick(b, (int)i0);
     case VINSAT_LA_ASSEMBLE: return launch_obs_assemble(b, d0);                   // d0 = alpha
     case VINSAT_LA_DYNAMICS:
-      VS_TRY(launch_dynamics_stm(ctx, b->n_pairs, b->dyn_order, b->st, b->gap, vc, (int)i0, b->drec, nullptr));
+      VS_TRY(launch_dynamics_stm(ctx, b->n_pairs, b->dyn_order, b->st, b->gap, vc, (int)i0, b->drec, nullptr, b->mrec));
       return launch_quat_terms(ctx, b->T, b->st, b->crot, b->gap, qc, b->drec);
     case VINSAT_LA_SYSTEM:
       b->srec_valid = true; b->last_sigma = d0; b->last_initialize = (int)i0; b->have_iter = true;

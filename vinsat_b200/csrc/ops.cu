@@ -139,7 +139,7 @@ int vinsat_predict(vinsat_ctx* ctx, int mem, int64_t n_frames, const double* sta
   VS_LAUNCH(ctx, F_LAYOUT, k_gaps, ceil_div(T, 256), 256, 0, T, ti.p, gap.p, err.p);
   if (jac || xp.p) {
     VS_CUDA(ctx, drec.alloc(T * VS_DREC));
-    VS_TRY(launch_dynamics_stm(ctx, T, nullptr, st.p, gap.p, vel_coeff, mode, drec.p, xp.p));
+    VS_TRY(launch_dynamics_stm(ctx, T, nullptr, st.p, gap.p, vel_coeff, mode, drec.p, xp.p, nullptr));
     VS_TRY(launch_quat_terms(ctx, T, st.p, cr.p, gap.p, quat_coeff, drec.p));
     VS_LAUNCH(ctx, F_LAYOUT, k_predict_extract, (unsigned)T, 64, 0, T, drec.p, rp.p, ph.p, qg.p, hd.p, ho.p);
   } else if (rp.p && T > 1) {
