@@ -30,7 +30,8 @@ UNIT = "solves/s"
 # algorithmic work per unit
 BYTES_PER_OBS_RESJAC = 156.0          # X 24 + uv 16 + frame id 4 read; r 16 + J(2x6) 96 written
 BYTES_PER_FRAME_STATE = 88.0          # state row (p,q) 56 + intrinsics 32, amortised over the frame's observations
-BYTES_PER_FRAME_SOLVE = 2880.0        # D,U,b read 1368 + W,y written 720 + W,y read 720 + delta written 72
+BYTES_PER_FRAME_SOLVE_FWD = 2088.0    # forward elimination: D,U,b read 1368 + W,y written 720
+BYTES_PER_FRAME_SOLVE_BWD = 792.0     # back-substitution: W,y read 720 + delta written 72
 BYTES_PER_FRAME_SOLVE_INIT = 288.0    # obs record read 216 + delta written 72
 FLOP_PER_RK4_STM_STEP = 1332.0        # DFMA*2+DMUL+DADD of one single-thread 6-column RK4+STM step (cuobjdump); the
                                       # shipped 2-thread x 3-column kernel executes 2012 (state stages duplicated)
@@ -272,7 +273,10 @@ def run_gpu(args):
         per_launch = {k: v[0] / v[1] for k, v in fam.items() if v[1]}
         kern = {}
         kern["blocktridiag_solve"] = dict(bound="hbm", unit="GB/s", peak=hbm_peak,
-                                          achieved=BYTES_PER_FRAME_SOLVE * n_frames / (per_launch.get("blocktridiag_solve", float("nan")) * 1e-3) / 1e9)
+                                          achieved=BYTES_PER_FRAME_SOLVE_FWD * n_frames / (per_launch.get("blocktridiag_solve", float("nan")) * 1e-3) / 1e9)
+        if "blocktridiag_backsub" in per_launch:
+            kern["blocktridiag_backsub"] = dict(bound="hbm", unit="GB/s", peak=hbm_peak,
+                                                achieved=BYTES_PER_FRAME_SOLVE_BWD * n_frames / (per_launch["blocktridiag_backsub"] * 1e-3) / 1e9)
         if "solve_init" in per_launch:
             kern["solve_init"] = dict(bound="hbm", unit="GB/s", peak=hbm_peak,
                                       achieved=BYTES_PER_FRAME_SOLVE_INIT * n_frames / (per_launch["solve_init"] * 1e-3) / 1e9)

@@ -34,6 +34,7 @@ void free_all(vinsat_batch* b) {
                   b->d_frame_off, b->d_obs_off, b->c_obs, b->wmax, b->lam, b->lam_next, b->lam32_last, b->init_res,
                   b->active, b->ntrials, b->sel_prefix, b->sel_rank, b->sel_hist, b->flags, b->seg_a, b->seg_b,
                   b->seg_left, b->seg_prob, b->seg_has_next, b->pl_a, b->pl_b, b->pl_prob, b->red_a, b->red_b,
+                  b->bb_a, b->bb_e, b->bb_dir, b->bb_prob, b->bb_mid, b->midrec,
                   b->redrec, b->rsys, b->rlow, b->rwrec, b->la_pack, b->la_gath, b->la_rsys, b->la_rlow, b->la_rwrec,
                   b->la_xsep, b->la_sums, b->la_edge, b->la_edges_all, b->la_chain};
   for (void* p : ptrs)
@@ -98,6 +99,7 @@ int build_frame_index(vinsat_batch* b, const vinsat_problem_desc* d, std::vector
 // Cut every problem into segments for the partitioned solve (kernels_chain.cu).  Depends only on frame_off.
 struct Segmentation {
   std::vector<int32_t> a, b, left, prob, has_next, pl_a, pl_b, pl_prob, red_a, red_b;
+  std::vector<int32_t> bb_a, bb_e, bb_dir, bb_prob, bb_mid;
   bool partitioned = false;
 };
 
@@ -128,6 +130,13 @@ Segmentation make_segments(const vinsat_ctx* ctx, int64_t P, const int64_t* fram
   for (int64_t p = 0; p < P; p++) {
     const int64_t f0 = frame_off[p], f1 = frame_off[p + 1], Tp = f1 - f0;
     s.pl_a.push_back((int32_t)f0); s.pl_b.push_back((int32_t)f1); s.pl_prob.push_back((int32_t)p);
+    {
+      const int32_t m = Tp > 0 ? (int32_t)(f0 + Tp / 2) : -1;
+      s.bb_a.push_back((int32_t)f0);     s.bb_e.push_back(Tp > 0 ? m : (int32_t)f0);     s.bb_dir.push_back(1);
+      s.bb_a.push_back((int32_t)f1 - 1); s.bb_e.push_back(Tp > 0 ? m : (int32_t)f1 - 1); s.bb_dir.push_back(-1);
+      s.bb_prob.push_back((int32_t)p); s.bb_prob.push_back((int32_t)p);
+      s.bb_mid.push_back(m); s.bb_mid.push_back(m);
+    }
     s.red_a.push_back((int32_t)s.a.size());
     if (Tp > 0) {
       int64_t S;
@@ -190,6 +199,8 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
     VS_CUDA(ctx, up(b->seg_prob, sg.prob)); VS_CUDA(ctx, up(b->seg_has_next, sg.has_next));
     VS_CUDA(ctx, up(b->pl_a, sg.pl_a)); VS_CUDA(ctx, up(b->pl_b, sg.pl_b)); VS_CUDA(ctx, up(b->pl_prob, sg.pl_prob));
     VS_CUDA(ctx, up(b->red_a, sg.red_a)); VS_CUDA(ctx, up(b->red_b, sg.red_b));
+    VS_CUDA(ctx, up(b->bb_a, sg.bb_a)); VS_CUDA(ctx, up(b->bb_e, sg.bb_e)); VS_CUDA(ctx, up(b->bb_dir, sg.bb_dir));
+    VS_CUDA(ctx, up(b->bb_prob, sg.bb_prob)); VS_CUDA(ctx, up(b->bb_mid, sg.bb_mid));
     VS_CUDA(ctx, cudaStreamSynchronize(s));     // the host vectors die at the end of this scope
   }
   VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, 4 * sizeof(int32_t), s));
@@ -253,6 +264,7 @@ static int create_impl(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t ow
 #define A(ptr, n) if (rc == VINSAT_OK) rc = dev_alloc(ctx, &b->ptr, (n))
   A(seg_a, NS); A(seg_b, NS); A(seg_left, NS); A(seg_prob, NS); A(seg_has_next, NS);
   A(pl_a, P); A(pl_b, P); A(pl_prob, P); A(red_a, P); A(red_b, P);
+  A(bb_a, 2 * P); A(bb_e, 2 * P); A(bb_dir, 2 * P); A(bb_prob, 2 * P); A(bb_mid, 2 * P); A(midrec, 2 * P * 96);
   A(redrec, NS * VS_RREC); A(rsys, NS * VS_SREC); A(rlow, NS * 81); A(rwrec, NS * VS_WREC);
   if (b->window) { A(la_pack, NS * (VS_RREC + VS_SREC)); A(la_sums, 4); A(la_edge, 20); }
   A(st, T * 10); A(st_new, T * 10); A(intr, T * 4); A(crot, T * 4); A(gap, T); A(fprob, T); A(dyn_order, T);

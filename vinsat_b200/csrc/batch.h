@@ -38,6 +38,9 @@ struct vinsat_batch {
   int32_t *seg_a = nullptr, *seg_b = nullptr, *seg_left = nullptr, *seg_prob = nullptr, *seg_has_next = nullptr;  // [n_seg]
   int32_t *pl_a = nullptr, *pl_b = nullptr, *pl_prob = nullptr;   // [P] whole-problem chains
   int32_t *red_a = nullptr, *red_b = nullptr;                     // [P] reduced chains (segment index ranges)
+  // two-sided sweep: chains 2p (top) / 2p+1 (bottom): first element, end sentinel (= middle), direction, problem, middle
+  int32_t *bb_a = nullptr, *bb_e = nullptr, *bb_dir = nullptr, *bb_prob = nullptr, *bb_mid = nullptr;   // [2P]
+  double* midrec = nullptr;                                       // [2P][96]
   double* redrec = nullptr;    // [n_seg][VS_RREC]
   double* rsys = nullptr;      // [n_seg][VS_SREC] reduced system rows
   double* rlow = nullptr;      // [n_seg][81] explicit lower blocks of the reduced system

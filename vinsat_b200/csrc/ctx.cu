@@ -10,7 +10,7 @@ namespace vs {
 
 const char* const kFamilyNames[F_COUNT] = {
     "project_resjac", "obs_residual", "select_median", "obs_assemble", "dynamics_stm", "quat_terms", "system_build",
-    "blocktridiag_solve", "solve_init", "retract", "trial_residual", "accept_reduce", "layout", "orbit_sim", "satcam", "peak"};
+    "blocktridiag_solve", "blocktridiag_backsub", "solve_init", "retract", "trial_residual", "accept_reduce", "layout", "orbit_sim", "satcam", "peak"};
 
 static std::mutex g_err_mu;
 static std::string g_err;

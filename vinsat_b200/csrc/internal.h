@@ -19,7 +19,8 @@ enum Family {
   F_DYNAMICS,         // RK4 + STM
   F_QUAT,             // quaternion smoothness gradient / Hessian blocks
   F_SYSTEM,           // block-tridiagonal system build
-  F_SOLVE,            // block-tridiagonal LU solve
+  F_SOLVE,            // block-tridiagonal LU solve: forward elimination (+ partition / reduced-system kernels)
+  F_SOLVE_BWD,        // block-tridiagonal LU solve: back-substitution of the whole-problem chains
   F_SOLVE_INIT,       // initialize phase: per-frame Cholesky
   F_RETRACT,          // retraction
   F_TRIAL,            // trial residual evaluation (obs + dynamics)

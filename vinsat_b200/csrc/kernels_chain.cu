@@ -24,6 +24,12 @@
 
 namespace vs {
 
+#define VS_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != VINSAT_OK) return _rc; \
+  } while (0)
+
 constexpr int kMS = 10;   // padded row stride of 9x9 blocks in shared memory (16-byte aligned rows)
 
 __device__ __forceinline__ double fast_rcp_c(double x) {
@@ -69,15 +75,65 @@ struct ChainArgs {
   double* delta;             // solution rows
   const int32_t* out_index;  // PLAIN: element -> row of delta (null = identity)
   double* lam32_last;        // [P] or null
+  // two-sided sweep (PLAIN only): chains 2p (top, dir +1) and 2p+1 (bottom, dir -1) of problem p meet at ch_mid
+  const int32_t* ch_dir = nullptr;     // direction of travel per chain, or null (= +1); ch_b is the exclusive end sentinel
+  const int32_t* ch_mid = nullptr;     // middle element per chain (or -1: empty problem), or null
+  double* mid = nullptr;               // [n_chains][VS_MIDREC]  Lo W (row-major 81) | Lo y (9) of the chain's last element
 };
+constexpr int VS_MIDREC = 96;
 
-constexpr int kFwdWarps = 4;
+
+// Block Gauss-Jordan on the augmented columns [S | ...] (one column per lane, 9 registers) with 3x3 pivot blocks
+// (position, rotation, velocity): three dependent pivot steps per element instead of nine.  The three pivot
+// columns are broadcast through shared memory, every lane inverts the 3x3 pivot block in closed form (adjugate,
+// one reciprocal) and updates its own column.  Lanes 0..8 must hold the columns of S.
+__device__ __forceinline__ void gj_block3(double (&a_)[9], const int c, double (*colk3)[3][kMS]) {
+#pragma unroll
+  for (int kb = 0; kb < 3; kb++) {
+    if (c >= 3 * kb && c < 3 * kb + 3) {
+      double* dst = colk3[kb & 1][c - 3 * kb];
+#pragma unroll
+      for (int r = 0; r < 9; r++) dst[r] = a_[r];
+    }
+    __syncwarp();
+    double pc[3][9];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double2* p2 = reinterpret_cast<const double2*>(colk3[kb & 1][j]);
+#pragma unroll
+      for (int r2 = 0; r2 < 4; r2++) { const double2 v = p2[r2]; pc[j][2 * r2] = v.x; pc[j][2 * r2 + 1] = v.y; }
+      pc[j][8] = colk3[kb & 1][j][8];
+    }
+    const int o = 3 * kb;
+    const double p00 = pc[0][o], p10 = pc[0][o + 1], p20 = pc[0][o + 2];
+    const double p01 = pc[1][o], p11 = pc[1][o + 1], p21 = pc[1][o + 2];
+    const double p02 = pc[2][o], p12 = pc[2][o + 1], p22 = pc[2][o + 2];
+    const double c00 = p11 * p22 - p12 * p21, c01 = p12 * p20 - p10 * p22, c02 = p10 * p21 - p11 * p20;
+    const double inv = fast_rcp_c(p00 * c00 + p01 * c01 + p02 * c02);
+    const double i00 = c00 * inv, i01 = (p02 * p21 - p01 * p22) * inv, i02 = (p01 * p12 - p02 * p11) * inv;
+    const double i10 = c01 * inv, i11 = (p00 * p22 - p02 * p20) * inv, i12 = (p02 * p10 - p00 * p12) * inv;
+    const double i20 = c02 * inv, i21 = (p01 * p20 - p00 * p21) * inv, i22 = (p00 * p11 - p01 * p10) * inv;
+    const double b0 = a_[o], b1 = a_[o + 1], b2 = a_[o + 2];
+    const double t0 = i00 * b0 + i01 * b1 + i02 * b2;
+    const double t1 = i10 * b0 + i11 * b1 + i12 * b2;
+    const double t2 = i20 * b0 + i21 * b1 + i22 * b2;
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      if (r == o) a_[r] = t0;
+      else if (r == o + 1) a_[r] = t1;
+      else if (r == o + 2) a_[r] = t2;
+      else a_[r] = fma(-pc[2][r], t2, fma(-pc[1][r], t1, fma(-pc[0][r], t0, a_[r])));
+    }
+  }
+}
+
+constexpr int kFwdWarps = 2;    // 2 chains per CTA: 2P chains spread evenly over the 148 SMs (4 per CTA left 27 % of the SMs with half the work)
 
 // ---------------------------------------------------------------------------------------------------------
 // forward elimination of one chain per warp.  SPIKE=true: segment mode (Z columns + left-part record).
 // ---------------------------------------------------------------------------------------------------------
 template <bool SPIKE>
-__global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
+__global__ void __launch_bounds__(kFwdWarps * 32, 16 / kFwdWarps) k_chain_forward(ChainArgs A) {
   __shared__ __align__(16) double s_col[kFwdWarps][2][3][kMS];
   __shared__ __align__(16) double s_M[kFwdWarps][9 * kMS];
   __shared__ __align__(16) double s_W[kFwdWarps][10 * 9];
@@ -87,6 +143,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
   const int prob = A.ch_prob[ch];
   if (A.active && !A.active[prob]) return;
   const int a = A.ch_a[ch], e = A.ch_b[ch];
+  const int dir = (!SPIKE && A.ch_dir) ? A.ch_dir[ch] : 1;
   const int left = SPIKE ? A.ch_left[ch] : -1;
   double lam32 = 0.0;
   if (A.lam) {
@@ -97,16 +154,24 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
   // column roles
   const bool isS = c < 9, isU = c >= 9 && c < 18, isB = c == 18, isZ = SPIKE && c >= 19 && c < 28;
   const int cc = isS ? c : (isU ? c - 9 : (isZ ? c - 19 : 0));       // column index inside its block
-  // offset of element (r, c) inside a system record
-  const int base = isS ? c : (isU ? 81 + (c - 9) : 162);
-  const int rstride = isB ? 1 : 9;
+  // offset of element (r, c) inside a system record.  A bottom chain (dir -1) couples element i to i-1 through
+  // A(i, i-1) = U_{i-1}^T: its U lanes read the record of element i-1, transposed (contiguous rows).
+  const bool rev = dir < 0;
+  const int base = isS ? c : (isU ? (rev ? 81 + (c - 9) * 9 : 81 + (c - 9)) : 162);
+  const int rstride = (isB || (isU && rev)) ? 1 : 9;
+  const int joff = (isU && rev) ? -1 : 0;
   const bool loads = isS || isU || isB;
   double (*colk3)[3][kMS] = s_col[warp];
   double* M = s_M[warp];
   double* Ws = s_W[warp];
   double* rr = SPIKE ? A.redrec + (int64_t)ch * VS_RREC : nullptr;
-  const int len = e - a;
+  const int len = (e - a) * dir;
+  double* midrec = (!SPIKE && A.mid) ? A.mid + (int64_t)ch * VS_MIDREC : nullptr;
 
+  if (midrec && len <= 0) {
+    for (int idx = lane; idx < 90; idx += 32) midrec[idx] = 0.0;
+    return;
+  }
   if (SPIKE && len == 0) {
     // no interior: the separator couples directly to the left separator.  Ll = Lo_left, Dl = bl = 0.
     for (int idx = lane; idx < 171; idx += 32) {
@@ -125,7 +190,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
 #pragma unroll
   for (int r = 0; r < 9; r++) { corr[r] = 0.0; nxt[r] = 0.0; a_[r] = 0.0; }
   if (loads) {
-    const double* rec = A.rec + (int64_t)a * VS_SREC;
+    const double* rec = A.rec + (int64_t)(a + joff) * VS_SREC;
 #pragma unroll
     for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
   }
@@ -141,7 +206,8 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
     }
   }
 
-  for (int i = a; i < e; i++) {
+  for (int i = a; i != e; i += dir) {
+    const bool more = (i + dir != e);
     // assemble the augmented column of element i:  S: D + lam I - Lo W;  U: fresh;  b: b - Lo y;  Z: -Lo Z
 #pragma unroll
     for (int r = 0; r < 9; r++) {
@@ -150,8 +216,8 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
       else if (isB || isZ) v -= corr[r];
       a_[r] = v;
     }
-    if (i + 1 < e && loads) {
-      const double* rec = A.rec + (int64_t)(i + 1) * VS_SREC;
+    if (more && loads) {
+      const double* rec = A.rec + (int64_t)(i + dir + joff) * VS_SREC;
 #pragma unroll
       for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
     }
@@ -163,46 +229,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
 #pragma unroll
       for (int r = 0; r < 9; r++) M[r * kMS + cc] = a_[r];       // M[k][r'] = U[k][r'] = Lo[r'][k]
     }
-    // Block Gauss-Jordan on [S | U | b | Z] with 3x3 pivot blocks (position, rotation, velocity): three dependent
-    // pivot steps per element instead of nine.  The three pivot columns are broadcast through shared memory,
-    // every lane inverts the 3x3 pivot block in closed form (adjugate, one reciprocal) and updates its column.
-#pragma unroll
-    for (int kb = 0; kb < 3; kb++) {
-      if (c >= 3 * kb && c < 3 * kb + 3) {
-        double* dst = colk3[kb & 1][c - 3 * kb];
-#pragma unroll
-        for (int r = 0; r < 9; r++) dst[r] = a_[r];
-      }
-      __syncwarp();
-      double pc[3][9];
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const double2* p2 = reinterpret_cast<const double2*>(colk3[kb & 1][j]);
-#pragma unroll
-        for (int r2 = 0; r2 < 4; r2++) { const double2 v = p2[r2]; pc[j][2 * r2] = v.x; pc[j][2 * r2 + 1] = v.y; }
-        pc[j][8] = colk3[kb & 1][j][8];
-      }
-      const int o = 3 * kb;
-      const double p00 = pc[0][o], p10 = pc[0][o + 1], p20 = pc[0][o + 2];
-      const double p01 = pc[1][o], p11 = pc[1][o + 1], p21 = pc[1][o + 2];
-      const double p02 = pc[2][o], p12 = pc[2][o + 1], p22 = pc[2][o + 2];
-      const double c00 = p11 * p22 - p12 * p21, c01 = p12 * p20 - p10 * p22, c02 = p10 * p21 - p11 * p20;
-      const double inv = fast_rcp_c(p00 * c00 + p01 * c01 + p02 * c02);
-      const double i00 = c00 * inv, i01 = (p02 * p21 - p01 * p22) * inv, i02 = (p01 * p12 - p02 * p11) * inv;
-      const double i10 = c01 * inv, i11 = (p00 * p22 - p02 * p20) * inv, i12 = (p02 * p10 - p00 * p12) * inv;
-      const double i20 = c02 * inv, i21 = (p01 * p20 - p00 * p21) * inv, i22 = (p00 * p11 - p01 * p10) * inv;
-      const double b0 = a_[o], b1 = a_[o + 1], b2 = a_[o + 2];
-      const double t0 = i00 * b0 + i01 * b1 + i02 * b2;
-      const double t1 = i10 * b0 + i11 * b1 + i12 * b2;
-      const double t2 = i20 * b0 + i21 * b1 + i22 * b2;
-#pragma unroll
-      for (int r = 0; r < 9; r++) {
-        if (r == o) a_[r] = t0;
-        else if (r == o + 1) a_[r] = t1;
-        else if (r == o + 2) a_[r] = t2;
-        else a_[r] = fma(-pc[2][r], t2, fma(-pc[1][r], t1, fma(-pc[0][r], t0, a_[r])));
-      }
-    }
+    gj_block3(a_, c, colk3);
     // publish W (lanes 9..17) and y (lane 18) for the S / b lanes; store W, y, Z
     if (isU || isB) {
 #pragma unroll
@@ -220,7 +247,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
     }
     __syncwarp();
     // corr = Lo_i x (W_c | y | Z_c): for element i+1, and (segment mode) for the separator's row after the loop
-    if (i + 1 < e || SPIKE) {
+    if (more || SPIKE || midrec) {
       if (isS || isB || isZ) {
         double v[9];
         if (isZ) {
@@ -237,6 +264,14 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
     __syncwarp();
   }
 
+  if (midrec) {
+    // contribution of this half to the middle element's row: Lo W (9x9) and Lo y
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      if (isS) midrec[r * 9 + c] = corr[r];
+      else if (isB) midrec[81 + r] = corr[r];
+    }
+  }
   if (SPIKE) {
     // left part of the separator's row: Dl = -Lo W, bl = -Lo y, Ll = -Lo Z (all from the last interior element)
 #pragma unroll
@@ -249,6 +284,241 @@ __global__ void __launch_bounds__(kFwdWarps * 32) k_chain_forward(ChainArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Forward elimination, THREE CHAINS PER WARP (default).  The one-column-per-lane kernel above is bound by the
+// L1/shared-memory data pipe (ncu: 238 shared wavefronts per frame for the pivot / Lo broadcasts, 75-95 % busy),
+// not by latency, so more resident chains do not help it.  Here a group of 10 lanes owns a chain and every lane
+// holds one column of EACH of [S | b], [U | -] (and [Z | -] in segment mode): a broadcast shared-memory read
+// now serves three chains, the 3x3 pivot inverse is shared by the lane's 2-3 columns, 29/30 column slots do
+// useful work (19/32 before), and W_l = S^-1 U_l stays in the lane that needs it for Lo W (no W round trip).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCPW = 3;      // chains per warp
+constexpr int kGL = 10;      // lanes per chain
+
+template <int NS>
+__device__ __forceinline__ void gj_block3_slots(double (&a)[NS][9], const int l, double (*colk3)[3][kMS]) {
+#pragma unroll
+  for (int kb = 0; kb < 3; kb++) {
+    if (l >= 3 * kb && l < 3 * kb + 3) {
+      double* dst = colk3[kb & 1][l - 3 * kb];
+#pragma unroll
+      for (int r = 0; r < 9; r++) dst[r] = a[0][r];
+    }
+    __syncwarp();
+    double pc[3][9];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const double2* p2 = reinterpret_cast<const double2*>(colk3[kb & 1][j]);
+#pragma unroll
+      for (int r2 = 0; r2 < 4; r2++) { const double2 v = p2[r2]; pc[j][2 * r2] = v.x; pc[j][2 * r2 + 1] = v.y; }
+      pc[j][8] = colk3[kb & 1][j][8];
+    }
+    const int o = 3 * kb;
+    const double p00 = pc[0][o], p10 = pc[0][o + 1], p20 = pc[0][o + 2];
+    const double p01 = pc[1][o], p11 = pc[1][o + 1], p21 = pc[1][o + 2];
+    const double p02 = pc[2][o], p12 = pc[2][o + 1], p22 = pc[2][o + 2];
+    const double c00 = p11 * p22 - p12 * p21, c01 = p12 * p20 - p10 * p22, c02 = p10 * p21 - p11 * p20;
+    const double inv = fast_rcp_c(p00 * c00 + p01 * c01 + p02 * c02);
+    const double i00 = c00 * inv, i01 = (p02 * p21 - p01 * p22) * inv, i02 = (p01 * p12 - p02 * p11) * inv;
+    const double i10 = c01 * inv, i11 = (p00 * p22 - p02 * p20) * inv, i12 = (p02 * p10 - p00 * p12) * inv;
+    const double i20 = c02 * inv, i21 = (p01 * p20 - p00 * p21) * inv, i22 = (p00 * p11 - p01 * p10) * inv;
+#pragma unroll
+    for (int sl = 0; sl < NS; sl++) {
+      const double b0 = a[sl][o], b1 = a[sl][o + 1], b2 = a[sl][o + 2];
+      const double t0 = i00 * b0 + i01 * b1 + i02 * b2;
+      const double t1 = i10 * b0 + i11 * b1 + i12 * b2;
+      const double t2 = i20 * b0 + i21 * b1 + i22 * b2;
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        if (r == o) a[sl][r] = t0;
+        else if (r == o + 1) a[sl][r] = t1;
+        else if (r == o + 2) a[sl][r] = t2;
+        else a[sl][r] = fma(-pc[2][r], t2, fma(-pc[1][r], t1, fma(-pc[0][r], t0, a[sl][r])));
+      }
+    }
+  }
+}
+
+constexpr int kF3Warps = 1;
+
+template <bool SPIKE>
+__global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
+  constexpr int NS = SPIKE ? 3 : 2;
+  __shared__ __align__(16) double s_col[kF3Warps][kCPW][2][3][kMS];
+  __shared__ __align__(16) double s_M[kF3Warps][kCPW][9 * kMS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = min(lane / kGL, kCPW - 1);
+  const bool spare = lane >= kCPW * kGL;              // lanes 30, 31 shadow lane 29 and never write
+  const int l = spare ? kGL - 1 : lane - g * kGL;
+  const int ch = (blockIdx.x * kF3Warps + warp) * kCPW + g;
+  bool valid = ch < A.n_chains;
+  int prob = 0, a = 0, e = 0, dir = 1, left = -1;
+  if (valid) {
+    prob = A.ch_prob[ch];
+    if (A.active && !A.active[prob]) valid = false;
+  }
+  if (valid) {
+    a = A.ch_a[ch]; e = A.ch_b[ch];
+    dir = (!SPIKE && A.ch_dir) ? A.ch_dir[ch] : 1;
+    left = SPIKE ? A.ch_left[ch] : -1;
+  }
+  const bool writer = valid && !spare;
+  double lam32 = 0.0;
+  if (valid && A.lam) {
+    lam32 = (double)(float)A.lam[prob];           // torch.eye(n)*lamda is float32
+    if (A.lam32_last && writer && l == 0) A.lam32_last[prob] = lam32;
+  }
+  const bool isS = l < 9;                         // slot 0: S column l (l < 9) or b (l == 9); slot 1: U column l; slot 2: Z column l
+  const bool rev = dir < 0;
+  // slot 0 / slot 1 offsets inside a system record.  A bottom chain (dir -1) couples element i to i-1 through
+  // A(i, i-1) = U_{i-1}^T: its U column is a (contiguous) row of the record of element i-1.
+  const int base0 = isS ? l : 162, rs0 = isS ? 9 : 1;
+  const int base1 = rev ? 81 + l * 9 : 81 + l, rs1 = rev ? 1 : 9, joff1 = rev ? -1 : 0;
+  double (*colk3)[3][kMS] = s_col[warp][g];
+  double* M = s_M[warp][g];
+  const int len = valid ? (e - a) * dir : 0;
+  double* rr = (SPIKE && valid) ? A.redrec + (int64_t)ch * VS_RREC : nullptr;
+  double* midrec = (!SPIKE && A.mid && valid) ? A.mid + (int64_t)ch * VS_MIDREC : nullptr;
+
+  if (writer && len <= 0) {
+    if (midrec) {
+      for (int idx = l; idx < 90; idx += kGL) midrec[idx] = 0.0;
+    }
+    if (SPIKE && len == 0) {
+      // no interior: the separator couples directly to the left separator.  Ll = Lo_left, Dl = bl = 0.
+      for (int idx = l; idx < 171; idx += kGL) {
+        double v = 0.0;
+        if (idx >= 81 && idx < 162 && left >= 0) {
+          const int r = (idx - 81) / 9, k = (idx - 81) % 9;
+          v = A.lrec ? A.lrec[(int64_t)left * 81 + r * 9 + k] : A.rec[(int64_t)left * VS_SREC + 81 + k * 9 + r];
+        }
+        rr[idx] = v;
+      }
+    }
+  }
+  int maxlen = max(len, 0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  if (maxlen == 0) return;
+
+  double av[NS][9], nxt0[9], nxt1[9], corr0[9], corr2[9];
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    corr0[r] = 0.0; corr2[r] = 0.0; nxt0[r] = 0.0; nxt1[r] = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < NS; sl++) av[sl][r] = (sl == 0 && r == l) ? 1.0 : 0.0;    // idle groups: harmless identity pivots
+  }
+  if (len > 0) {
+    const double* rec0 = A.rec + (int64_t)a * VS_SREC;
+    const double* rec1 = A.rec + (int64_t)(a + joff1) * VS_SREC;
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      nxt0[r] = rec0[base0 + r * rs0];
+      nxt1[r] = isS ? rec1[base1 + r * rs1] : 0.0;
+    }
+    if (SPIKE && isS && left >= 0) {
+      // Z~_a = Lo_left, column l; kept NEGATED in corr2 because the assembly below uses a2 = -corr2
+      if (A.lrec) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) corr2[r] = -A.lrec[(int64_t)left * 81 + r * 9 + l];
+      } else {
+#pragma unroll
+        for (int r = 0; r < 9; r++) corr2[r] = -A.rec[(int64_t)left * VS_SREC + 81 + l * 9 + r];
+      }
+    }
+  }
+
+  for (int s = 0; s < maxlen; s++) {
+    const bool on = s < len;
+    const bool more = s + 1 < len;
+    const int i = a + dir * s;
+    if (on) {
+      // assemble the columns of element i:  S: D + lam I - Lo W;  b: b - Lo y;  U: fresh;  Z: -Lo Z
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        av[0][r] = nxt0[r] + ((isS && r == l) ? lam32 : 0.0) - corr0[r];
+        av[1][r] = nxt1[r];
+        if (SPIKE) av[NS - 1][r] = -corr2[r];
+      }
+    }
+    if (more) {
+      const double* rec0 = A.rec + (int64_t)(i + dir) * VS_SREC;
+      const double* rec1 = A.rec + (int64_t)(i + dir + joff1) * VS_SREC;
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        nxt0[r] = rec0[base0 + r * rs0];
+        if (isS) nxt1[r] = rec1[base1 + r * rs1];
+      }
+    }
+    // lower block Lo_i staged as M[k*kMS + r] = Lo_i[r][k]
+    if (on) {
+      if (A.lrec) {
+        if (!spare) {
+          const double* L = A.lrec + (int64_t)i * 81;
+          for (int idx = l; idx < 81; idx += kGL) { const int r = idx / 9, k = idx % 9; M[k * kMS + r] = L[idx]; }
+        }
+      } else if (isS) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) M[r * kMS + l] = av[1][r];       // M[k][r'] = U[k][r'] = Lo[r'][k]
+      }
+    }
+    gj_block3_slots<NS>(av, l, colk3);
+    if (on && writer) {
+      double* w = A.wrec + (int64_t)i * VS_WREC;
+      if (isS) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) w[l * 9 + r] = av[1][r];
+        if (SPIKE) {
+#pragma unroll
+          for (int r = 0; r < 9; r++) w[90 + l * 9 + r] = av[NS - 1][r];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 9; r++) w[81 + r] = av[0][r];
+      }
+    }
+    __syncwarp();      // M complete (and the pivot buffers free) before the products below
+    // corr = Lo_i x (W_l | y | Z_l): for element i+1 and, after the last element, for the middle / separator row
+    if (on && (more || SPIKE || midrec)) {
+      double v[9];
+#pragma unroll
+      for (int k = 0; k < 9; k++) v[k] = isS ? av[1][k] : av[0][k];
+      matvec9(M, v, corr0);
+      if (SPIKE) matvec9(M, av[NS - 1], corr2);
+      if (!more && writer) {
+        if (midrec) {
+          // contribution of this half to the middle element's row: Lo W (9x9) and Lo y
+#pragma unroll
+          for (int r = 0; r < 9; r++) {
+            if (isS) midrec[r * 9 + l] = corr0[r];
+            else midrec[81 + r] = corr0[r];
+          }
+        }
+        if (SPIKE) {
+          // left part of the separator's row: Dl = -Lo W, bl = -Lo y, Ll = -Lo Z (from the last interior element)
+#pragma unroll
+          for (int r = 0; r < 9; r++) {
+            if (isS) { rr[r * 9 + l] = -corr0[r]; rr[81 + r * 9 + l] = -corr2[r]; }
+            else rr[162 + r] = -corr0[r];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <bool SPIKE>
+static int launch_forward(vinsat_ctx* ctx, const ChainArgs& A) {
+  static const bool v1 = getenv("VINSAT_FWD_V1") != nullptr;
+  if (v1) {
+    VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<SPIKE>, ceil_div(A.n_chains, kFwdWarps), kFwdWarps * 32, 0, A);
+  } else {
+    VS_LAUNCH(ctx, F_SOLVE, k_chain_forward3<SPIKE>, ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
+  }
+  return VINSAT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // plain chains: backward substitution x_i = y_i - W_i x_{i+1}; lane r < 9 owns row r.  The per-frame work is
 // ~150 cycles but a W record comes from HBM (~800 cycles), so records are streamed through a shared-memory ring
 // with cp.async, kRing frames ahead.
@@ -257,40 +527,77 @@ constexpr int kRing = 8;
 
 __global__ void __launch_bounds__(128) k_chain_backward(ChainArgs A) {
   __shared__ __align__(16) double s_ring[4][kRing][96];
+  __shared__ __align__(16) double s_col[4][2][3][kMS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x * 4 + warp;
   if (ch >= A.n_chains) return;
-  if (A.active && !A.active[A.ch_prob[ch]]) return;
+  const int prob = A.ch_prob[ch];
+  if (A.active && !A.active[prob]) return;
   const int a = A.ch_a[ch], e = A.ch_b[ch];
-  if (e <= a) return;
+  const int dir = A.ch_dir ? A.ch_dir[ch] : 1;
+  const int len = (e - a) * dir;
+  const int mid = A.ch_mid ? A.ch_mid[ch] : -1;
+  if (len <= 0 && mid < 0) return;
   double (*ring)[96] = s_ring[warp];
-  auto issue = [&](int i, int slot) {          // W (81) | y (9) of element i -> ring[slot][0..90)
-    if (i >= a) {
-      const double* w = A.wrec + (int64_t)i * VS_WREC;
+  // elements are visited from the chain's last one (next to the sentinel e) back to its first: i_s = e - dir - dir*s
+  auto issue = [&](int s, int slot) {          // W (81) | y (9) of the s-th visited element -> ring[slot][0..90)
+    if (s < len) {
+      const double* w = A.wrec + (int64_t)(e - dir - dir * s) * VS_WREC;
       for (int idx = lane; idx < 90; idx += 32) __pipeline_memcpy_async(&ring[slot][idx], w + idx, 8);
     }
     __pipeline_commit();
   };
 #pragma unroll
-  for (int d = 0; d < kRing; d++) issue(e - 1 - d, d);
+  for (int d = 0; d < kRing; d++) issue(d, d);
   double dn[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) dn[k] = 0.0;
+  bool have_dn = false;
+  if (mid >= 0) {
+    // two-sided sweep: both halves solve the middle element's 9x9 system (identical arithmetic in both warps)
+    //   (D_m + lam I - Lo W|top - Lo W|bottom) x_m = b_m - Lo y|top - Lo y|bottom
+    const double* mt = A.mid + (int64_t)(ch & ~1) * VS_MIDREC;
+    const double* mb = A.mid + (int64_t)(ch | 1) * VS_MIDREC;
+    const double* rec = A.rec + (int64_t)mid * VS_SREC;
+    const double lam32 = A.lam ? (double)(float)A.lam[prob] : 0.0;
+    double col[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) {
+      double v = 0.0;
+      if (lane < 9) v = rec[r * 9 + lane] + (r == lane ? lam32 : 0.0) - mt[r * 9 + lane] - mb[r * 9 + lane];
+      else if (lane == 9) v = rec[162 + r] - mt[81 + r] - mb[81 + r];
+      else if (lane < 18) v = (r == lane - 9) ? 1.0 : 0.0;     // idle lanes carry harmless finite columns
+      col[r] = v;
+    }
+    gj_block3(col, lane, s_col[warp]);
+#pragma unroll
+    for (int k = 0; k < 9; k++) dn[k] = __shfl_sync(0xffffffffu, col[k], 9);
+    have_dn = true;
+    if ((ch & 1) == 0 && lane < 9) {
+      const int64_t row = A.out_index ? A.out_index[mid] : mid;
+      double xm = 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) xm = (lane == k) ? dn[k] : xm;
+      A.delta[row * 9 + lane] = xm;
+    }
+  }
   int slot = 0;
-  for (int i = e - 1; i >= a; i--) {
+  for (int s = 0; s < len; s++) {
+    const int i = e - dir - dir * s;
     __pipeline_wait_prior(kRing - 1);
     __syncwarp();
     double dr = 0.0;
     if (lane < 9) {
       const double* w = ring[slot];
       dr = w[81 + lane];
-      if (i + 1 < e) {
+      if (have_dn) {
 #pragma unroll
         for (int k = 0; k < 9; k++) dr = fma(-w[k * 9 + lane], dn[k], dr);
       }
     }
+    have_dn = true;
     __syncwarp();
-    issue(i - kRing, slot);
+    issue(s + kRing, slot);
 #pragma unroll
     for (int k = 0; k < 9; k++) dn[k] = __shfl_sync(0xffffffffu, dr, k);
     const int64_t row = A.out_index ? A.out_index[i] : i;
@@ -500,7 +807,7 @@ int launch_seg_forward(vinsat_batch* b) {
   vinsat_ctx* ctx = b->ctx;
   if (b->n_seg == 0) return VINSAT_OK;
   ChainArgs A = seg_args(b);
-  VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<true>, ceil_div(A.n_chains, kFwdWarps), kFwdWarps * 32, 0, A);
+  VS_TRY(launch_forward<true>(ctx, A));
   VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
   return VINSAT_OK;
 }
@@ -530,7 +837,7 @@ int launch_reduced_packed(vinsat_batch* b, int64_t S_total, const double* pack, 
   R.delta = xsep;
   R.out_index = nullptr;
   R.lam32_last = nullptr;
-  VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<false>, 1, kFwdWarps * 32, 0, R);
+  VS_TRY(launch_forward<false>(ctx, R));
   VS_LAUNCH(ctx, F_SOLVE, k_chain_backward, 1, 128, 0, R);
   return VINSAT_OK;
 }
@@ -549,15 +856,24 @@ int launch_chain_solve(vinsat_batch* b) {
   A.lam32_last = b->lam32_last;
   A.redrec = b->redrec;
   if (!b->partitioned) {
-    A.n_chains = (int)b->P;
-    A.ch_a = b->pl_a; A.ch_b = b->pl_b; A.ch_left = nullptr; A.ch_prob = b->pl_prob;
-    VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<false>, ceil_div(A.n_chains, kFwdWarps), kFwdWarps * 32, 0, A);
-    VS_LAUNCH(ctx, F_SOLVE, k_chain_backward, ceil_div(A.n_chains, 4), 128, 0, A);
+    static const bool one_sided = getenv("VINSAT_ONE_SIDED_SWEEP") != nullptr;
+    if (one_sided) {
+      A.n_chains = (int)b->P;
+      A.ch_a = b->pl_a; A.ch_b = b->pl_b; A.ch_left = nullptr; A.ch_prob = b->pl_prob;
+    } else {
+      // two-sided sweep: a top chain and a bottom chain per problem eliminate towards the middle frame
+      // (same flops as the one-sided sweep, twice the independent chains, half the sequential length)
+      A.n_chains = (int)(2 * b->P);
+      A.ch_a = b->bb_a; A.ch_b = b->bb_e; A.ch_left = nullptr; A.ch_prob = b->bb_prob;
+      A.ch_dir = b->bb_dir; A.ch_mid = b->bb_mid; A.mid = b->midrec;
+    }
+    VS_TRY(launch_forward<false>(ctx, A));
+    VS_LAUNCH(ctx, F_SOLVE_BWD, k_chain_backward, ceil_div(A.n_chains, 4), 128, 0, A);
     return VINSAT_OK;
   }
   A.n_chains = (int)b->n_seg;
   A.ch_a = b->seg_a; A.ch_b = b->seg_b; A.ch_left = b->seg_left; A.ch_prob = b->seg_prob;
-  VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<true>, ceil_div(A.n_chains, kFwdWarps), kFwdWarps * 32, 0, A);
+  VS_TRY(launch_forward<true>(ctx, A));
   VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
   VS_LAUNCH(ctx, F_SOLVE, k_reduced_build, ceil_div((int64_t)b->n_seg * 192, 256), 256, 0, (int)b->n_seg, b->seg_b,
             b->seg_left, b->seg_prob, b->seg_has_next, b->active, b->lam, b->srec, b->redrec, b->rsys, b->rlow);
@@ -573,7 +889,7 @@ int launch_chain_solve(vinsat_batch* b) {
   R.delta = b->delta;
   R.out_index = b->seg_b;          // separator s -> frame b_s
   R.lam32_last = nullptr;
-  VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<false>, ceil_div(R.n_chains, kFwdWarps), kFwdWarps * 32, 0, R);
+  VS_TRY(launch_forward<false>(ctx, R));
   VS_LAUNCH(ctx, F_SOLVE, k_chain_backward, ceil_div(R.n_chains, 4), 128, 0, R);
   VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div((int64_t)b->n_seg, 4), 128, 0, (int)b->n_seg, b->seg_a, b->seg_b,
             b->seg_left, b->seg_prob, b->active, b->wrec, b->delta);
