@@ -4,6 +4,10 @@
 // Layout: observations are SoA (X[3][M], uv[2][M], conf[M], oframe[M]) sorted by frame, so a warp reads
 // 32 consecutive doubles per array (fully coalesced 256 B requests); per-frame data (state row 80 B,
 // intrinsics 32 B) is AoS and is broadcast-read by the lanes that share a frame (L1 hits).
+#include <cuda_pipeline.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -465,10 +469,8 @@ __global__ void __launch_bounds__(128, kMinBlocks) k_obs_assemble_cam(int64_t T,
 // tile (LDS latency instead of L2/HBM latency per observation) and the un-normalised weights are written back
 // through the same tile, coalesced.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kStageThreads = 128;
-constexpr int kStageChunk = 1408;     // observations per chunk: 6 arrays x 1408 x 8 B = 67.6 KB (3 CTAs per SM)
-
-__global__ void __launch_bounds__(kStageThreads, 3) k_obs_assemble_staged(int64_t T, int64_t M,
+template <int kStageThreads, int kStageChunk, int kUnroll, int kMinBlocks>
+__global__ void __launch_bounds__(kStageThreads, kMinBlocks) k_obs_assemble_staged(int64_t T, int64_t M,
                                                                          const int32_t* __restrict__ obs_start,
                                                                          const int32_t* __restrict__ fprob,
                                                                          const double* __restrict__ X,
@@ -487,6 +489,23 @@ __global__ void __launch_bounds__(kStageThreads, 3) k_obs_assemble_staged(int64_
   const bool valid = f < T;
   const int kb = obs_start[f0];
   const int ke = obs_start[min(f0 + kStageThreads, T)];
+  // asynchronous staging (cp.async, no register round trip): every copy of the chunk is in flight at once and
+  // overlaps the per-frame prologue below (ncu of the synchronous version: 2/3 of the stall samples sat on the
+  // staging loop's load->store pairs and on the prologue's dependent loads)
+  auto issue_chunk = [&](int base) {
+    const int n = min(kStageChunk, ke - base);
+    for (int i = tid; i < n; i += kStageThreads) {
+      const int k = base + i;
+      __pipeline_memcpy_async(&tile[i], &X[k], 8);
+      __pipeline_memcpy_async(&tile[kStageChunk + i], &X[M + k], 8);
+      __pipeline_memcpy_async(&tile[2 * kStageChunk + i], &X[2 * M + k], 8);
+      __pipeline_memcpy_async(&tile[3 * kStageChunk + i], &uv[k], 8);
+      __pipeline_memcpy_async(&tile[4 * kStageChunk + i], &uv[M + k], 8);
+      __pipeline_memcpy_async(&tile[5 * kStageChunk + i], &conf[k], 8);
+    }
+    __pipeline_commit();
+  };
+  issue_chunk(kb);
   int k0 = 0, k1 = 0;
   double sN[5] = {0, 0, 0, 0, 0}, sNH[9], sHNH[6] = {0, 0, 0, 0, 0, 0}, sm[3] = {0, 0, 0}, sHm[3] = {0, 0, 0}, sabs = 0.0;
 #pragma unroll
@@ -516,17 +535,10 @@ __global__ void __launch_bounds__(kStageThreads, 3) k_obs_assemble_staged(int64_
   }
   for (int base = kb; base < ke; base += kStageChunk) {
     const int n = min(kStageChunk, ke - base);
-    for (int i = tid; i < n; i += kStageThreads) {
-      const int k = base + i;
-      tile[i] = X[k];
-      tile[kStageChunk + i] = X[M + k];
-      tile[2 * kStageChunk + i] = X[2 * M + k];
-      tile[3 * kStageChunk + i] = uv[k];
-      tile[4 * kStageChunk + i] = uv[M + k];
-      tile[5 * kStageChunk + i] = conf[k];
-    }
+    __pipeline_wait_prior(0);
     __syncthreads();
     const int lo = max(k0, base), hi = min(k1, base + n);
+#pragma unroll kUnroll
     for (int k = lo; k < hi; k++) {
       const int i = k - base;
       const double dx = tile[i] - px, dy = tile[kStageChunk + i] - py, dz = tile[2 * kStageChunk + i] - pz;
@@ -560,6 +572,7 @@ __global__ void __launch_bounds__(kStageThreads, 3) k_obs_assemble_staged(int64_
     __syncthreads();
     for (int i = tid; i < n; i += kStageThreads) wu_out[base + i] = tile[5 * kStageChunk + i];
     __syncthreads();
+    if (base + kStageChunk < ke) issue_chunk(base + kStageChunk);
   }
   if (valid) {
     const double N[9] = {sN[0], 0.0, sN[1], 0.0, sN[2], sN[3], sN[1], sN[3], sN[4]};
@@ -613,17 +626,26 @@ int launch_obs_assemble(vinsat_batch* b, double alpha) {
   VS_LAUNCH(ctx, F_OBS_ASSEMBLE, (k_obs_assemble_cam<G, MB>), ceil_div(b->T * G, 128), 128, 0, b->T, b->M, b->obs_start, \
             b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax)
 #define CAM_LAUNCH(G) CAM_LAUNCH2(G, 3)
-  if (variant == 0 || variant == 30) {
-    static bool attr_set = false;
-    const int smem = 6 * kStageChunk * (int)sizeof(double);
-    if (!attr_set) {
-      VS_CUDA(ctx, cudaFuncSetAttribute(k_obs_assemble_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
-    VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_staged, ceil_div(b->T, kStageThreads), kStageThreads, smem, b->T, b->M,
-              b->obs_start, b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
-    return VINSAT_OK;
-  }
+#define STAGED_LAUNCH(TH, CH, UN, MB)                                                                                          \
+  do {                                                                                                                 \
+    static bool attr_set = false;                                                                                      \
+    const int smem = 6 * CH * (int)sizeof(double);                                                                     \
+    if (!attr_set) {                                                                                                   \
+      VS_CUDA(ctx, cudaFuncSetAttribute(k_obs_assemble_staged<TH, CH, UN, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    VS_LAUNCH(ctx, F_OBS_ASSEMBLE, (k_obs_assemble_staged<TH, CH, UN, MB>), ceil_div(b->T, TH), TH, smem, b->T, b->M,          \
+              b->obs_start, b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);    \
+    return VINSAT_OK;                                                                                                  \
+  } while (0)
+  if (variant == 30) STAGED_LAUNCH(128, 1408, 1, 3);     // 67.6 KB, 3 CTAs per SM
+  if (variant == 31) STAGED_LAUNCH(64, 704, 1, 6);       // 33.8 KB, 6 CTAs per SM
+  if (variant == 0 || variant == 32) STAGED_LAUNCH(32, 352, 1, 12);      // default: one warp per CTA, 16.9 KB, 12 CTAs per SM
+  if (variant == 33) STAGED_LAUNCH(32, 352, 2, 12);
+  if (variant == 34) STAGED_LAUNCH(32, 352, 2, 8);
+  if (variant == 35) STAGED_LAUNCH(32, 352, 1, 16);
+  if (variant == 36) STAGED_LAUNCH(32, 352, 2, 16);
+#undef STAGED_LAUNCH
   if (variant == 9) { if (sparse) CAM_LAUNCH2(1, 4); else CAM_LAUNCH(8); return VINSAT_OK; }
   if (variant == 10) { CAM_LAUNCH(1); return VINSAT_OK; }
   if (variant == 11) { CAM_LAUNCH(2); return VINSAT_OK; }
