@@ -30,7 +30,7 @@ UNIT = "solves/s"
 # algorithmic work per unit
 BYTES_PER_OBS_RESJAC = 156.0          # X 24 + uv 16 + frame id 4 read; r 16 + J(2x6) 96 written
 BYTES_PER_FRAME_STATE = 88.0          # state row (p,q) 56 + intrinsics 32, amortised over the frame's observations
-BYTES_PER_FRAME_SOLVE_FWD = 2088.0    # forward elimination: D,U,b read 1368 + W,y written 720
+BYTES_PER_FRAME_SOLVE_FWD = 1792.0    # forward elimination with the fused system build: grec 224 + drec 512 + mrec 336 read, W,y written 720
 BYTES_PER_FRAME_SOLVE_BWD = 792.0     # back-substitution: W,y read 720 + delta written 72
 BYTES_PER_FRAME_SOLVE_INIT = 288.0    # obs record read 216 + delta written 72
 FLOP_PER_RK4_STM_STEP = 1332.0        # DFMA*2+DMUL+DADD of one single-thread 6-column RK4+STM step (cuobjdump); the

@@ -363,10 +363,13 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
   // the full records are only materialised on demand (last_hessian / debug_fetch).
   // The plain (unpartitioned) sweep builds its columns on the fly from the per-frame records (fused system
   // build); the partitioned sweep and the diagnostics read the materialised records.
-  if (!initialize) VS_TRY(launch_system_build(b, 0, Sigma, vel_coeff));
-  b->srec_valid = !initialize;
+  static const bool no_fuse = getenv("VINSAT_NO_FUSED_SYSTEM") != nullptr || getenv("VINSAT_ONE_SIDED_SWEEP") != nullptr;
+  b->fused_system = !initialize && !b->partitioned && !no_fuse;
+  if (!initialize && !b->fused_system) VS_TRY(launch_system_build(b, 0, Sigma, vel_coeff));
+  b->srec_valid = !initialize && !b->fused_system;
   b->last_sigma = Sigma;
   b->cur_sigma = Sigma;
+  b->cur_vc = vel_coeff;
   VS_TRY(launch_init_residual(b, initialize, Sigma, 0.0, lam_dev_in));
   for (int trial = 0; trial < 16; trial++) {
     VS_TRY(launch_solve_retract(b, initialize));

@@ -5,7 +5,7 @@
 // Per-frame record sizes (doubles).
 #define VS_GREC 28    // obs normal block: 21 sym (6x6 upper) + 6 rhs + 1 sum|r|
 #define VS_DREC 64    // dynamics: Phi 36 | r6 6 | rho 1 | qgrad 3 | Hq_diag 9 | Hq_off 9
-#define VS_MREC 28    // Phi^T D^2 Phi (21, upper triangle) | Phi^T D r (6) | pad  (written by k_dynamics_stm)
+#define VS_MREC 42    // Phi^T D^2 Phi (6x6, both triangles, [a*6+b]) | Phi^T D r (6)  (written by k_dynamics_stm)
 #define VS_SREC 172   // system: D 81 | U 81 | b 9 | pad 1
 #define VS_WREC 172   // solver: W = S^-1 U (col-major 81) | y 9 | Z spike (col-major 81) | pad
 #define VS_RREC 342   // reduced-system contributions of a segment: left {Dl 81, Ll 81, bl 9} | right {Dr 81, Ur 81, br 9}
@@ -91,6 +91,8 @@ struct vinsat_batch {
   bool have_iter = false;
   bool srec_valid = false;
   double last_sigma = 0.0;
-  double cur_sigma = 0.0;      // Sigma of the iteration in flight (fused forward sweep)
+  double cur_sigma = 0.0;      // Sigma / velocity weight of the iteration in flight (fused forward sweep)
+  double cur_vc = 100.0;
+  bool fused_system = false;   // the sweep builds its columns from grec/drec/mrec (no srec round trip)
   int last_initialize = 0;
 };

@@ -60,6 +60,149 @@ __device__ __forceinline__ void matvec9(const double* __restrict__ M, const doub
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused system build: the normal-equation blocks of frame f are assembled on the fly, one column per lane, from
+// the per-frame records the assembly kernels leave behind (BA_filtering.py:28-48) -- no [D | U | b]
+// record is written to / read back from HBM (1376 B + 1368 B per frame):
+//   grec[f]  sum_k w J^T J (upper triangle 21) | sum_k w J^T r (6) | sum |r|          (k_obs_assemble)
+//   drec[f]  Phi 36 | r 6 | rho | qgrad 3 | Hq_diag 9 | Hq_off 9                      (k_dynamics_stm, k_quat_terms)
+//   mrec[f]  Phi^T D^2 Phi 36 | Phi^T D r 6                                           (k_dynamics_stm)
+// ---------------------------------------------------------------------------------------------------------
+struct FusedSrc {
+  const double* grec = nullptr;
+  const double* drec = nullptr;
+  const double* mrec = nullptr;
+  const int32_t* gap = nullptr;
+  const unsigned long long* wmax = nullptr;   // [P] bit pattern of the largest raw weight
+  double Sigma = 0.0, vc = 100.0;
+};
+
+__device__ __forceinline__ int sym6(int a, int b) { return a * 6 - (a * (a - 1)) / 2 + (b - a); }   // a <= b
+
+// column l of D_f without damping (l < 9) or the right-hand side b_f (l == 9)
+__device__ __forceinline__ void fused_col0(const FusedSrc& S, const int64_t f, const int l, const double invw,
+                                           double (&out)[9]) {
+  const double* G = S.grec + f * VS_GREC;
+  const double* Dr = S.drec + f * VS_DREC;
+  const double* Mm = S.mrec + f * VS_MREC;
+  const bool isb = l == 9, pos = l < 3, rot = l >= 3 && l < 6, pv = (l < 9) && !rot;
+  const int pl = pos ? l : l - 3;
+  const bool hn = S.gap[f] > 0;
+  const bool hp = f > 0 && S.gap[f - 1] > 0;
+  const double vc2 = S.vc * S.vc;
+  const double sN = hn ? (isb ? -S.Sigma : S.Sigma) : 0.0;
+  double g[6], m[6], h[3], e[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const int gidx = isb ? 21 + j : (j <= l ? sym6(j, l) : sym6(l, j));
+    g[j] = (l < 6 || isb) ? invw * G[gidx] : 0.0;
+    m[j] = (pv || isb) ? sN * Mm[(isb ? 6 : pl) * 6 + j] : 0.0;
+    e[j] = 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) h[j] = rot ? S.Sigma * Dr[46 + j * 3 + (l - 3)] : (isb ? -S.Sigma * Dr[43 + j] : 0.0);
+  if (isb && hp) {
+    const double* rp = S.drec + (f - 1) * VS_DREC + 36;
+#pragma unroll
+    for (int j = 0; j < 6; j++) e[j] = S.Sigma * (j < 3 ? 1.0 : S.vc) * rp[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    out[j] = g[j] + m[j] + e[j];
+    out[3 + j] = g[3 + j] + h[j];
+    out[6 + j] = m[3 + j] + e[3 + j];
+  }
+  if (pv && hp) {
+    const double dd = S.Sigma * (pos ? 1.0 : vc2);
+#pragma unroll
+    for (int r = 0; r < 9; r++) out[r] += (r == l) ? dd : 0.0;
+  }
+}
+
+// The sweep kernel splits the build in two so that no arithmetic waits on a load inside the latency chain:
+// fused_load() only ISSUES the (predicated, lane-specific) loads of element i+1 before the elimination of element
+// i, fused_combine() turns the raw values into the two columns one iteration later, in registers.
+struct FusedRaw {
+  double g[6];    // grec: column l of the observation block (l < 6) or J^T W r (b lane)
+  double m[6];    // mrec: column pl of Phi^T D^2 Phi (pos / vel lanes) or Phi^T D r (b lane)
+  double h[3];    // drec: column of Hq_diag (rot lanes) or qgrad (b lane)
+  double x[6];    // drec: Phi entries of the coupling block (pos / vel), Hq_off column (rot), r of the pair before (b)
+  int gn, gp;     // gap[f], gap[f-1] (0 at the first frame)
+};
+
+struct FusedLane {   // loop-invariant lane constants
+  int gi[6];
+  int mo, ho, hs, xo, xs, xn;
+  bool pg, pm, ph, isb, pos, rot, pv;
+};
+
+__device__ __forceinline__ FusedLane fused_lane(const int l, const int dir) {
+  FusedLane L;
+  L.isb = l == 9; L.pos = l < 3; L.rot = l >= 3 && l < 6; L.pv = (l < 9) && !L.rot;
+  const int pl = L.pos ? l : l - 3, cl = l - 3;
+#pragma unroll
+  for (int j = 0; j < 6; j++) L.gi[j] = L.isb ? 21 + j : (l < 6 ? (j <= l ? sym6(j, l) : sym6(l, j)) : 0);
+  L.pg = l < 6 || L.isb;
+  L.pm = L.pv || L.isb;
+  L.mo = L.isb ? 36 : (L.pv ? pl * 6 : 0);
+  L.ph = L.rot || L.isb;
+  L.ho = L.rot ? 46 + cl : 43; L.hs = L.rot ? 3 : 1;
+  if (L.isb) { L.xo = 36; L.xs = 1; L.xn = 6; }
+  else if (L.rot) { L.xo = dir > 0 ? 55 + cl : 55 + cl * 3; L.xs = dir > 0 ? 3 : 1; L.xn = 3; }
+  else { L.xo = dir > 0 ? pl * 6 : pl; L.xs = dir > 0 ? 1 : 6; L.xn = 6; }
+  return L;
+}
+
+__device__ __forceinline__ void fused_load(const FusedSrc& S, const FusedLane& L, const int64_t f, const int dir,
+                                           FusedRaw& R) {
+  const double* G = S.grec + f * VS_GREC;
+  const double* Dr = S.drec + f * VS_DREC;
+  const double* Mm = S.mrec + f * VS_MREC;
+  // coupling block: this frame's record (forward) or the previous frame's (reverse; also r of the pair before)
+  const int64_t fx = (L.isb || dir < 0) ? f - 1 : f;
+  const double* Dx = S.drec + fx * VS_DREC;
+  R.gn = S.gap[f];
+  R.gp = f > 0 ? S.gap[f - 1] : 0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    R.g[j] = L.pg ? G[L.gi[j]] : 0.0;
+    R.m[j] = L.pm ? Mm[L.mo + j] : 0.0;
+    R.x[j] = (fx >= 0 && j < L.xn) ? Dx[L.xo + j * L.xs] : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) R.h[j] = L.ph ? Dr[L.ho + j * L.hs] : 0.0;
+}
+
+__device__ __forceinline__ void fused_combine(const FusedSrc& S, const FusedLane& L, const FusedRaw& R, const int l,
+                                              const int dir, const double invw, double (&out0)[9], double (&out1)[9]) {
+  const bool hn = R.gn > 0, hp = R.gp > 0;
+  const double vc2 = S.vc * S.vc;
+  const double sN = hn ? (L.isb ? -S.Sigma : S.Sigma) : 0.0;
+  const double ch = L.rot ? S.Sigma : -S.Sigma;                       // h is zero outside rot / b lanes
+  const double ep = (L.isb && hp) ? S.Sigma : 0.0, ev = ep * S.vc;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    out0[j] = invw * R.g[j] + sN * R.m[j] + ep * R.x[j];
+    out0[3 + j] = invw * R.g[3 + j] + ch * R.h[j];
+    out0[6 + j] = sN * R.m[3 + j] + ev * R.x[3 + j];
+  }
+  const double dd = (L.pv && hp) ? S.Sigma * (L.pos ? 1.0 : vc2) : 0.0;
+#pragma unroll
+  for (int r = 0; r < 9; r++) out0[r] += (r == l) ? dd : 0.0;
+  const bool on = dir > 0 ? hn : hp;
+  const double sg = (on && !L.isb) ? S.Sigma : 0.0;
+  // forward: U[r][l] = -Sigma dv2[pl] Phi[pl][pr];  reverse: U_{i-1}[l][r] = -Sigma dv2[pr] Phi[pr][pl]
+  const double cp = L.pv ? -sg * (dir > 0 ? (L.pos ? 1.0 : vc2) : 1.0) : 0.0;
+  const double cv = L.pv ? -sg * (dir > 0 ? (L.pos ? 1.0 : vc2) : vc2) : 0.0;
+  const double cr = L.rot ? sg : 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    out1[j] = cp * R.x[j];
+    out1[3 + j] = cr * R.x[j];
+    out1[6 + j] = cv * R.x[3 + j];
+  }
+}
+
 struct ChainArgs {
   int n_chains;
   const int32_t* ch_a;       // first element
@@ -79,6 +222,8 @@ struct ChainArgs {
   const int32_t* ch_dir = nullptr;     // direction of travel per chain, or null (= +1); ch_b is the exclusive end sentinel
   const int32_t* ch_mid = nullptr;     // middle element per chain (or -1: empty problem), or null
   double* mid = nullptr;               // [n_chains][VS_MIDREC]  Lo W (row-major 81) | Lo y (9) of the chain's last element
+  int fused = 0;                       // 1: rec is null, columns come from `fs` (fused system build)
+  FusedSrc fs;
 };
 constexpr int VS_MIDREC = 96;
 
@@ -340,7 +485,7 @@ __device__ __forceinline__ void gj_block3_slots(double (&a)[NS][9], const int l,
 
 constexpr int kF3Warps = 1;
 
-template <bool SPIKE>
+template <bool SPIKE, bool FUSED>
 __global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
   constexpr int NS = SPIKE ? 3 : 2;
   __shared__ __align__(16) double s_col[kF3Warps][kCPW][2][3][kMS];
@@ -407,13 +552,25 @@ __global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
 #pragma unroll
     for (int sl = 0; sl < NS; sl++) av[sl][r] = (sl == 0 && r == l) ? 1.0 : 0.0;    // idle groups: harmless identity pivots
   }
+  double invw = 0.0;
+  if (FUSED && valid) {
+    const unsigned long long wb = A.fs.wmax[prob];
+    invw = wb ? 1.0 / __longlong_as_double((long long)wb) : 0.0;
+  }
+  FusedLane FL;
+  FusedRaw FR;
+  if (FUSED) FL = fused_lane(l, dir);
   if (len > 0) {
-    const double* rec0 = A.rec + (int64_t)a * VS_SREC;
-    const double* rec1 = A.rec + (int64_t)(a + joff1) * VS_SREC;
+    if (FUSED) {
+      fused_load(A.fs, FL, a, dir, FR);
+    } else {
+      const double* rec0 = A.rec + (int64_t)a * VS_SREC;
+      const double* rec1 = A.rec + (int64_t)(a + joff1) * VS_SREC;
 #pragma unroll
-    for (int r = 0; r < 9; r++) {
-      nxt0[r] = rec0[base0 + r * rs0];
-      nxt1[r] = isS ? rec1[base1 + r * rs1] : 0.0;
+      for (int r = 0; r < 9; r++) {
+        nxt0[r] = rec0[base0 + r * rs0];
+        nxt1[r] = isS ? rec1[base1 + r * rs1] : 0.0;
+      }
     }
     if (SPIKE && isS && left >= 0) {
       // Z~_a = Lo_left, column l; kept NEGATED in corr2 because the assembly below uses a2 = -corr2
@@ -431,6 +588,7 @@ __global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
     const bool on = s < len;
     const bool more = s + 1 < len;
     const int i = a + dir * s;
+    if (FUSED && on) fused_combine(A.fs, FL, FR, l, dir, invw, nxt0, nxt1);
     if (on) {
       // assemble the columns of element i:  S: D + lam I - Lo W;  b: b - Lo y;  U: fresh;  Z: -Lo Z
 #pragma unroll
@@ -441,12 +599,16 @@ __global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
       }
     }
     if (more) {
-      const double* rec0 = A.rec + (int64_t)(i + dir) * VS_SREC;
-      const double* rec1 = A.rec + (int64_t)(i + dir + joff1) * VS_SREC;
+      if (FUSED) {
+        fused_load(A.fs, FL, i + dir, dir, FR);
+      } else {
+        const double* rec0 = A.rec + (int64_t)(i + dir) * VS_SREC;
+        const double* rec1 = A.rec + (int64_t)(i + dir + joff1) * VS_SREC;
 #pragma unroll
-      for (int r = 0; r < 9; r++) {
-        nxt0[r] = rec0[base0 + r * rs0];
-        if (isS) nxt1[r] = rec1[base1 + r * rs1];
+        for (int r = 0; r < 9; r++) {
+          nxt0[r] = rec0[base0 + r * rs0];
+          if (isS) nxt1[r] = rec1[base1 + r * rs1];
+        }
       }
     }
     // lower block Lo_i staged as M[k*kMS + r] = Lo_i[r][k]
@@ -510,10 +672,14 @@ __global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
 template <bool SPIKE>
 static int launch_forward(vinsat_ctx* ctx, const ChainArgs& A) {
   static const bool v1 = getenv("VINSAT_FWD_V1") != nullptr;
-  if (v1) {
+  if (v1 && !A.fused) {
     VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<SPIKE>, ceil_div(A.n_chains, kFwdWarps), kFwdWarps * 32, 0, A);
   } else {
-    VS_LAUNCH(ctx, F_SOLVE, k_chain_forward3<SPIKE>, ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
+    if (A.fused) {
+      VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<false, true>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
+    } else {
+      VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<SPIKE, false>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
+    }
   }
   return VINSAT_OK;
 }
@@ -558,14 +724,24 @@ __global__ void __launch_bounds__(128) k_chain_backward(ChainArgs A) {
     //   (D_m + lam I - Lo W|top - Lo W|bottom) x_m = b_m - Lo y|top - Lo y|bottom
     const double* mt = A.mid + (int64_t)(ch & ~1) * VS_MIDREC;
     const double* mb = A.mid + (int64_t)(ch | 1) * VS_MIDREC;
-    const double* rec = A.rec + (int64_t)mid * VS_SREC;
     const double lam32 = A.lam ? (double)(float)A.lam[prob] : 0.0;
-    double col[9];
+    double col[9], own[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) own[r] = 0.0;
+    if (A.fused) {
+      const unsigned long long wb = A.fs.wmax[prob];
+      const double invw = wb ? 1.0 / __longlong_as_double((long long)wb) : 0.0;
+      if (lane < 10) fused_col0(A.fs, mid, lane, invw, own);
+    } else {
+      const double* rec = A.rec + (int64_t)mid * VS_SREC;
+#pragma unroll
+      for (int r = 0; r < 9; r++) own[r] = lane < 9 ? rec[r * 9 + lane] : (lane == 9 ? rec[162 + r] : 0.0);
+    }
 #pragma unroll
     for (int r = 0; r < 9; r++) {
       double v = 0.0;
-      if (lane < 9) v = rec[r * 9 + lane] + (r == lane ? lam32 : 0.0) - mt[r * 9 + lane] - mb[r * 9 + lane];
-      else if (lane == 9) v = rec[162 + r] - mt[81 + r] - mb[81 + r];
+      if (lane < 9) v = own[r] + (r == lane ? lam32 : 0.0) - mt[r * 9 + lane] - mb[r * 9 + lane];
+      else if (lane == 9) v = own[r] - mt[81 + r] - mb[81 + r];
       else if (lane < 18) v = (r == lane - 9) ? 1.0 : 0.0;     // idle lanes carry harmless finite columns
       col[r] = v;
     }
@@ -866,6 +1042,11 @@ int launch_chain_solve(vinsat_batch* b) {
       A.n_chains = (int)(2 * b->P);
       A.ch_a = b->bb_a; A.ch_b = b->bb_e; A.ch_left = nullptr; A.ch_prob = b->bb_prob;
       A.ch_dir = b->bb_dir; A.ch_mid = b->bb_mid; A.mid = b->midrec;
+      if (b->fused_system) {
+        A.fused = 1; A.rec = nullptr;
+        A.fs.grec = b->grec; A.fs.drec = b->drec; A.fs.mrec = b->mrec; A.fs.gap = b->gap; A.fs.wmax = b->wmax;
+        A.fs.Sigma = b->cur_sigma; A.fs.vc = b->cur_vc;
+      }
     }
     VS_TRY(launch_forward<false>(ctx, A));
     VS_LAUNCH(ctx, F_SOLVE_BWD, k_chain_backward, ceil_div(A.n_chains, 4), 128, 0, A);

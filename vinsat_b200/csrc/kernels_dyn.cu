@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(128) k_dynamics_stm(int64_t n_pairs, const int
       double wcol[6];                                   // D^2 Phi[:, a]
 #pragma unroll
       for (int k = 0; k < 6; k++) wcol[k] = dv1[k] * dv1[k] * phi[c][k];
-      // entries (a, b) with b >= a: own columns b = a .. 3*half+2, and (half 0 only) the partner's columns 3..5
+      // entries (a, b) with b >= a: own columns b = a .. 3*half+2, and (half 0 only) the partner's columns 3..5;
+      // every entry is stored at both (a, b) and (b, a) so the 6x6 block is exactly symmetric
 #pragma unroll
       for (int c2 = 0; c2 < 3; c2++) {
         if (c2 >= c) {
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(128) k_dynamics_stm(int64_t n_pairs, const int
 #pragma unroll
           for (int k = 0; k < 6; k++) sacc = fma(wcol[k], phi[c2][k], sacc);
           const int bcol = half * 3 + c2;
-          if (live) m[a * 6 - (a * (a - 1)) / 2 + (bcol - a)] = sacc;
+          if (live) { m[a * 6 + bcol] = sacc; m[bcol * 6 + a] = sacc; }
         }
       }
       if (half == 0) {
@@ -91,15 +92,14 @@ __global__ void __launch_bounds__(128) k_dynamics_stm(int64_t n_pairs, const int
 #pragma unroll
           for (int k = 0; k < 6; k++) sacc = fma(wcol[k], other[c2][k], sacc);
           const int bcol = 3 + c2;
-          if (live) m[a * 6 - (a * (a - 1)) / 2 + (bcol - a)] = sacc;
+          if (live) { m[a * 6 + bcol] = sacc; m[bcol * 6 + a] = sacc; }
         }
       }
       double vacc = 0.0;
 #pragma unroll
       for (int k = 0; k < 6; k++) vacc = fma(phi[c][k] * dv1[k], r6[k], vacc);
-      if (live) m[21 + a] = vacc;
+      if (live) m[36 + a] = vacc;
     }
-    if (live && half == 1) m[27] = 0.0;
   }
 }
 
