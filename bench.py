@@ -33,8 +33,9 @@ BYTES_PER_FRAME_STATE = 88.0          # state row (p,q) 56 + intrinsics 32, amor
 BYTES_PER_FRAME_SOLVE_FWD = 1792.0    # forward elimination with the fused system build: grec 224 + drec 512 + mrec 336 read, W,y written 720
 BYTES_PER_FRAME_SOLVE_BWD = 792.0     # back-substitution: W,y read 720 + delta written 72
 BYTES_PER_FRAME_SOLVE_INIT = 288.0    # obs record read 216 + delta written 72
-FLOP_PER_RK4_STM_STEP = 1332.0        # DFMA*2+DMUL+DADD of one single-thread 6-column RK4+STM step (cuobjdump); the
-                                      # shipped 2-thread x 3-column kernel executes 2012 (state stages duplicated)
+FLOP_PER_RK4_STM_STEP = 1146.0        # one RK4 step of the 6-state + its 6x6 STM, FMA = 2: 4 x 60
+                                      # (acceleration + gravity gradient) + 78 (state stages) + 6 x 138 (STM columns);
+                                      # the shipped 2-thread x 3-column kernel executes 1464 (trajectory duplicated)
 
 
 def workload(args):

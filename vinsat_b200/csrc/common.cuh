@@ -123,8 +123,8 @@ __device__ __forceinline__ void accel_grad(double x, double y, double z, double&
                                            double* g) {
   const double x2 = x * x, y2 = y * y, z2 = z * z;
   const double n2 = x2 + y2 + z2;
-  const double inv_n2 = 1.0 / n2;
   const double inv_n = rsqrt(n2);
+  const double inv_n2 = inv_n * inv_n;      // one rsqrt, no division (2 ulp; the STM tolerance is 1e-9 relative)
   const double inv_n3 = inv_n * inv_n2;
   const double inv_n5 = inv_n3 * inv_n2;
   const double inv_n7 = inv_n5 * inv_n2;
@@ -132,23 +132,19 @@ __device__ __forceinline__ void accel_grad(double x, double y, double z, double&
   const double k = -kMu * inv_n3, j = kJ2 * inv_n7;
   const double sx = 6.0 * x2 - 1.5 * y2 - 1.5 * z2;
   const double sz = 3.0 * x2 - 4.5 * y2 - 4.5 * z2;
-  ax = k * x + j * sx * x;
-  ay = k * y + j * sx * y;
-  az = k * z + j * sz * z;
-  const double r[3] = {x, y, z};
-  const double s[3] = {sx, sx, sz};
-  const double M[3][3] = {{6.0, -1.5, -1.5}, {6.0, -1.5, -1.5}, {3.0, -4.5, -4.5}};
-  const double t3 = 3.0 * kMu * inv_n5, t7 = -7.0 * kJ2 * inv_n9;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      double rr = r[i] * r[c];
-      double v = t3 * rr + t7 * s[i] * rr + j * 2.0 * M[i][c] * rr;
-      if (i == c) v += k + j * s[i];
-      g[i * 3 + c] = v;
-    }
-  }
+  // accel_i = r_i (k + j s_i);  G_ic = r_i r_c (3 mu/n^5 - 7 J2 s_i/n^9 + 2 j M_ic) + delta_ic (k + j s_i), factored
+  // so that every entry is one product of r_i r_c with one of four row/column coefficients
+  const double dxy = k + j * sx, dz = k + j * sz;
+  ax = dxy * x;
+  ay = dxy * y;
+  az = dz * z;
+  const double t3 = 3.0 * kMu * inv_n5, t7 = -7.0 * kJ2 * inv_n9, j2 = 2.0 * j;
+  const double cx = t3 + t7 * sx, cz = t3 + t7 * sz;
+  const double cxa = cx + 6.0 * j2, cxb = cx - 1.5 * j2, cza = cz + 3.0 * j2, czb = cz - 4.5 * j2;
+  const double xy = x * y, xz = x * z, yz = y * z;
+  g[0] = x2 * cxa + dxy; g[1] = xy * cxb;       g[2] = xz * cxb;
+  g[3] = xy * cxa;       g[4] = y2 * cxb + dxy; g[5] = yz * cxb;
+  g[6] = xz * cza;       g[7] = yz * czb;       g[8] = z2 * czb + dz;
 }
 
 // One classic RK4 step of the 6-state (BA_utils.py:901-912).
