@@ -132,7 +132,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     w = workload(args)
-    n = 4 * max(cores, 1) if args.cpu_problems <= 0 else args.cpu_problems
+    n = 8 * max(cores, 1) if args.cpu_problems <= 0 else args.cpu_problems
     vals = []
     cb = None
     for _ in range(max(args.warmup, 0)):
@@ -311,7 +311,7 @@ def run_gpu(args):
         cb = None
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
-            cb = cpu_baseline(T, K, 4 * cores if args.cpu_problems <= 0 else args.cpu_problems, cores)
+            cb = cpu_baseline(T, K, 8 * cores if args.cpu_problems <= 0 else args.cpu_problems, cores)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
