@@ -109,16 +109,35 @@ __global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const in
     const int comp = i >= Mp ? 1 : 0;
     sel_keys[i] = (unsigned long long)__double_as_longlong(fabs(r[(int64_t)comp * M + k0 + (i - comp * Mp)]));
   }
-  if (tid == 0) { s_prefix = 0ull; s_rank = (unsigned long long)((n - 1) / 2); }
-  const int shifts[6] = {53, 42, 31, 20, 9, 0};
-  const int nbits[6] = {11, 11, 11, 11, 11, 9};
+  // Bits that are identical in every key carry no information: find the highest differing bit with a block-wide
+  // OR of (key ^ key0) and start the 11-bit digits THERE.  (Starting at bit 63 the first digit is the sign + top
+  // exponent bits, which take 3-4 distinct values => the shared-memory atomics serialise 32-way, and a pass is
+  // wasted.)
+  __shared__ unsigned long long s_diff;
+  if (tid == 0) s_diff = 0ull;
+  __syncthreads();
+  {
+    const unsigned long long key0 = sel_keys[0];
+    unsigned long long d = 0ull;
+    for (int i = tid; i < n; i += kSelThreads) d |= sel_keys[i] ^ key0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d |= __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == 0 && d) atomicOr(&s_diff, d);
+  }
+  __syncthreads();
+  const unsigned long long diff = s_diff;
+  int hi = diff ? 64 - __clzll((long long)diff) : 0;        // digits cover bits [0, hi)
+  if (tid == 0) {
+    s_prefix = hi >= 64 ? 0ull : ((sel_keys[0] >> hi) << hi);
+    s_rank = (unsigned long long)((n - 1) / 2);
+  }
 #pragma unroll 1
-  for (int pass = 0; pass < 6; pass++) {
+  while (hi > 0) {
+    const int nb = min(11, hi), shift = hi - nb, hs = hi;
     for (int i = tid; i < kSelBins; i += kSelThreads) hist[i] = 0;
     __syncthreads();
     const unsigned long long pre = s_prefix;
-    const int shift = shifts[pass], hs = shift + nbits[pass];
-    const unsigned int dmask = (1u << nbits[pass]) - 1u;
+    const unsigned int dmask = (1u << nb) - 1u;
     for (int i = tid; i < n; i += kSelThreads) {
       const unsigned long long key = sel_keys[i];
       const bool match = hs >= 64 ? true : ((key >> hs) == (pre >> hs));
@@ -148,6 +167,7 @@ __global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const in
       s_rank = rk - (bin == 2 * tid ? before : before + h0);
     }
     __syncthreads();
+    hi = shift;
   }
   if (tid == 0) c_obs[p] = __longlong_as_double((long long)s_prefix);
 }
