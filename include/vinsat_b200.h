@@ -94,6 +94,23 @@ int vinsat_propagate_chain(vinsat_ctx* ctx, int mem, int64_t n_steps, double dt,
 int vinsat_orbit_propagate(vinsat_ctx* ctx, int mem, int64_t n_traj, int64_t n_steps, int64_t stride, double h,
                            const double* x0, double* out);
 
+/* ---- a4 / (f)3: input preparation (BA/BA_utils.py:278-288, 1361-1367; od_pipe.py:944-953) -------
+ * vinsat_cum_rotations: compute_omega_from_quat on the full-rate quaternions quat_full [n_full,4] (xyzw), then
+ * for every frame the ordered product of exp(dt*omega_s) over its gap s = time_idx[i] .. time_idx[i+1]-1 --
+ * exactly precompute_cum_rotations(omegas, dt)[0, :, -1], the only slice `predict` reads (BA_utils.py:295); the
+ * last frame gets the identity.  omega_out [n_full,3] nullable, cum_rot_out [n_frames,4].
+ * vinsat_precompute_cum_rotations: the general form, omegas [n_frames, n_slots, 3] -> cum_out [n_frames, n_slots, 4]. */
+int vinsat_cum_rotations(vinsat_ctx* ctx, int mem, int64_t n_full, const double* quat_full, double dt,
+                         int64_t n_frames, const int64_t* time_idx, double* omega_out, double* cum_rot_out);
+int vinsat_precompute_cum_rotations(vinsat_ctx* ctx, int mem, int64_t n_frames, int64_t n_slots, const double* omegas,
+                                    double dt, double* cum_out);
+
+/* ---- a11 / (f)3: batched rigid-body attitude simulation (trajgen_pipe.py:155-207, attitude_step) ----
+ * State [q (scalar FIRST, as the reference's L(q)), omega] = 7 doubles; inertia_diag [3] = diag(J) (HOST pointer).
+ * out [n_traj, n_steps/stride + 1, 7]. */
+int vinsat_attitude_propagate(vinsat_ctx* ctx, int mem, int64_t n_traj, int64_t n_steps, int64_t stride, double h,
+                              const double* inertia_diag, const double* x0, double* out);
+
 /* ---- batched BA / OD (BA/BA_filtering.py:4-98 driven by od_pipe.py:1036-1040) -----------------------
  * A batch holds P independent problems, concatenated; problem p owns frames
  * [frame_off[p], frame_off[p+1]) and observations [obs_off[p], obs_off[p+1]).  `ii` holds frame indices

@@ -70,7 +70,7 @@ def test_host_helpers_vs_reference_golden():
     assert eq(U.quaternion_exp(torch.tensor(g["d"])), g["qexp"])
     assert np.abs(U.quaternion_log(torch.tensor(g["q1"])).numpy() - g["qlog"]).max() < 1e-14
     assert eq(U.attitude_jacobian(torch.tensor(g["q1"])), g["Gq"])
-    assert eq(U.precompute_cum_rotations(torch.tensor(g["omegas"]), 1.0), g["cum_rot"])
+    assert eq(hm.precompute_cum_rotations(g["omegas"], 1.0), g["cum_rot"])      # device version: tests/test_gpu_prep.py
     assert np.abs(U.compute_omega_from_quat(torch.tensor(g["qtrack"]), 1.0).numpy() - g["omega_from_quat"]).max() < 1e-12
     assert np.array_equal(hm.convert_pos_to_quaternion(g["pos"]), g["nadir_quat"])
     assert np.array_equal(hm.compute_velocity_from_pos(g["pos"], 1.0), g["vel_fd"])

@@ -162,12 +162,17 @@ def attitude_jacobian(q):
 
 
 def precompute_cum_rotations(omegas, dt):
-    """BA_utils.py:278-288: (1,T,N,3) -> (1,T,N,4)."""
-    rot = hm.quaternion_exp(dt * _np(omegas))
-    out = [rot[:, :, 0]]
-    for i in range(1, rot.shape[2]):
-        out.append(hm.quaternion_multiply(out[-1], rot[:, :, i]))
-    return torch.from_numpy(np.stack(out, axis=-2))
+    """BA_utils.py:278-288: (1,T,N,3) -> (1,T,N,4), on the device (`vinsat_precompute_cum_rotations`)."""
+    om = _np(omegas)
+    return torch.from_numpy(_ctx().precompute_cum_rotations(om[0], dt)[None])
+
+
+def cum_rotations_from_quat(gt_quat_full, time_idx, dt):
+    """The slice of precompute_cum_rotations that `predict` reads (BA_utils.py:295), straight from the full-rate
+    quaternions: compute_omega_from_quat + per-gap product on the device (od_pipe.py:944-953 without the
+    (1,T,N,3) zero-padded omegas tensor).  Returns (cum_rot (T,4), gt_omega (n_full,3))."""
+    cr, om = _ctx().cum_rotations(_np(gt_quat_full), np.asarray(time_idx), dt, want_omega=True)
+    return cr, torch.from_numpy(om)
 
 
 def compute_omega_from_quat(quat, dt):

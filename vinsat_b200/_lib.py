@@ -50,6 +50,12 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p]),
     "vinsat_orbit_propagate": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double,
                                          C.c_void_p, C.c_void_p]),
+    "vinsat_cum_rotations": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_int64, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "vinsat_precompute_cum_rotations": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_double,
+                                                  C.c_void_p]),
+    "vinsat_attitude_propagate": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "vinsat_batch_create": (C.c_int, [C.c_void_p, C.POINTER(ProblemDesc), C.POINTER(C.c_void_p)]),
     "vinsat_batch_create_window": (C.c_int, [C.c_void_p, C.POINTER(ProblemDesc), C.c_int64, C.c_int64, C.c_int64,
                                              C.POINTER(C.c_void_p)]),
@@ -225,6 +231,34 @@ class Context:
         out = np.empty((x0.shape[0], n_steps // stride + 1, 6))
         self.check(self.lib.vinsat_orbit_propagate(self.h, MEM_HOST, x0.shape[0], int(n_steps), int(stride),
                                                    float(h), _ptr(x0), _ptr(out)))
+        return out
+
+    def cum_rotations(self, quat_full, time_idx, dt=1.0, want_omega=False):
+        """compute_omega_from_quat + precompute_cum_rotations(...)[0, :, -1] (od_pipe.py:944-953) on the device."""
+        q, ti = f64(quat_full).reshape(-1, 4), i64(time_idx)
+        n, T = q.shape[0], ti.shape[0]
+        om = np.empty((n, 3)) if want_omega else None
+        cr = np.empty((T, 4))
+        self.check(self.lib.vinsat_cum_rotations(self.h, MEM_HOST, n, _ptr(q), float(dt), T, _ptr(ti), _ptr(om),
+                                                 _ptr(cr)))
+        return (cr, om) if want_omega else cr
+
+    def precompute_cum_rotations(self, omegas, dt=1.0):
+        """BA_utils.py:278-288: omegas (T, N, 3) -> cumulative rotations (T, N, 4)."""
+        om = f64(omegas)
+        T, N = om.shape[0], om.shape[1]
+        out = np.empty((T, N, 4))
+        self.check(self.lib.vinsat_precompute_cum_rotations(self.h, MEM_HOST, T, N, _ptr(om), float(dt), _ptr(out)))
+        return out
+
+    def attitude_propagate(self, x0, n_steps, stride=1, h=1.0, inertia_diag=None):
+        """Batched trajgen_pipe.attitude_step: x0 (n,7) [q scalar-first, omega] -> (n, n_steps/stride+1, 7)."""
+        x0 = f64(x0).reshape(-1, 7)
+        J = f64(inertia_diag if inertia_diag is not None else
+                (1 / 3) * np.array([(.1 ** 2 + .34 ** 2), (.1 ** 2 + .34 ** 2), (.1 ** 2 + .1 ** 2)]))
+        out = np.empty((x0.shape[0], n_steps // stride + 1, 7))
+        self.check(self.lib.vinsat_attitude_propagate(self.h, MEM_HOST, x0.shape[0], int(n_steps), int(stride),
+                                                      float(h), _ptr(J), _ptr(x0), _ptr(out)))
         return out
 
     def satcam_project(self, poses, landmarks_ecef, hfov, w_px, h_px, want_uv=True, want_mask=True,

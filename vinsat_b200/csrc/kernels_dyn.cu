@@ -121,56 +121,87 @@ __device__ __forceinline__ double sgn(double d) { return (double)((d > 0.0) - (d
 __device__ __forceinline__ Quat load_q(const double* s) { return Quat{s[3], s[4], s[5], s[6]}; }
 __device__ __forceinline__ Quat load_q4(const double* s) { return Quat{s[0], s[1], s[2], s[3]}; }
 
-__global__ void __launch_bounds__(128) k_quat_terms(int64_t T, const double* __restrict__ st,
-                                                    const double* __restrict__ crot,
-                                                    const int32_t* __restrict__ gap, double c,
-                                                    double* __restrict__ drec) {
-  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (f >= T) return;
-  const bool has_next = gap[f] > 0;
-  const bool has_prev = f > 0 && gap[f - 1] > 0;
-  const Quat q = load_q(st + f * 10);
-  const Quat qc = qconj(q);
-  double ax = 0, ay = 0, az = 0, aw = 0, rho = 0;
-  double* d = drec + f * VS_DREC;
-  if (has_next) {
-    const Quat qn = load_q(st + (f + 1) * 10);
-    const Quat R = load_q4(crot + f * 4);
-    const Quat Rc = qconj(R);
-    const double dt = qdot(qmul(q, R), qn);
-    const double s = sgn(dt);
-    rho = c * (1.0 - fabs(dt));
-    const Quat m = qmul(qn, Rc);                    // M(R)^T q_{i+1}
-    ax += -c * s * m.x; ay += -c * s * m.y; az += -c * s * m.z; aw += -c * s * m.w;
-    // Hq[i,i+1] column j = -c s vec(conj(q) (x) ((q_next (x) e_j) (x) conj(R)))
-    const Quat e[3] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}};
+// One thread per frame; the state rows / cumulative rotations of the CTA's 128 frames (+ one halo row each side)
+// are staged with coalesced loads and the 22 outputs per frame leave through a shared tile as contiguous runs
+// (the direct version issued 22 stores + 14 loads per thread that each touched 32 sectors: ncu lg_throttle).
+constexpr int kQtFrames = 128;
+constexpr int kQtOut = 23;      // 22 outputs, odd pitch
+
+__global__ void __launch_bounds__(kQtFrames) k_quat_terms(int64_t T, const double* __restrict__ st,
+                                                          const double* __restrict__ crot,
+                                                          const int32_t* __restrict__ gap, double c,
+                                                          double* __restrict__ drec) {
+  __shared__ double s_q[(kQtFrames + 2) * 4];      // quaternion of frames f0-1 .. f0+128
+  __shared__ double s_r[(kQtFrames + 1) * 4];      // cum rotation of frames f0-1 .. f0+127
+  __shared__ int32_t s_gap[kQtFrames + 1];         // gap of frames f0-1 .. f0+127
+  __shared__ double s_out[kQtFrames * kQtOut];
+  const int tid = threadIdx.x;
+  const int64_t f0 = (int64_t)blockIdx.x * kQtFrames;
+  const int nf = (int)min((int64_t)kQtFrames, T - f0);
+  for (int i = tid; i < (kQtFrames + 2) * 4; i += kQtFrames) {
+    const int64_t f = f0 - 1 + i / 4;
+    s_q[i] = (f >= 0 && f < T) ? st[f * 10 + 3 + (i & 3)] : 0.0;
+  }
+  for (int i = tid; i < (kQtFrames + 1) * 4; i += kQtFrames) {
+    const int64_t f = f0 - 1 + i / 4;
+    s_r[i] = (f >= 0 && f < T) ? crot[f * 4 + (i & 3)] : 0.0;
+  }
+  for (int i = tid; i < kQtFrames + 1; i += kQtFrames) {
+    const int64_t f = f0 - 1 + i;
+    s_gap[i] = (f >= 0 && f < T) ? gap[f] : 0;
+  }
+  __syncthreads();
+  if (tid < nf) {
+    const bool has_next = s_gap[tid + 1] > 0;
+    const bool has_prev = s_gap[tid] > 0;
+    const Quat q = load_q4(s_q + (tid + 1) * 4);
+    const Quat qc = qconj(q);
+    double ax = 0, ay = 0, az = 0, aw = 0, rho = 0;
+    double* d = s_out + tid * kQtOut - 42;           // d[42..63] as in the record
+    if (has_next) {
+      const Quat qn = load_q4(s_q + (tid + 2) * 4);
+      const Quat R = load_q4(s_r + (tid + 1) * 4);
+      const Quat Rc = qconj(R);
+      const double dt = qdot(qmul(q, R), qn);
+      const double s = sgn(dt);
+      rho = c * (1.0 - fabs(dt));
+      const Quat m = qmul(qn, Rc);                    // M(R)^T q_{i+1}
+      ax += -c * s * m.x; ay += -c * s * m.y; az += -c * s * m.z; aw += -c * s * m.w;
+      // Hq[i,i+1] column j = -c s vec(conj(q) (x) ((q_next (x) e_j) (x) conj(R)))
+      const Quat e[3] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}};
 #pragma unroll
-    for (int jx = 0; jx < 3; jx++) {
-      const Quat v = qmul(qc, qmul(qmul(qn, e[jx]), Rc));
-      d[55 + 0 * 3 + jx] = -c * s * v.x;
-      d[55 + 1 * 3 + jx] = -c * s * v.y;
-      d[55 + 2 * 3 + jx] = -c * s * v.z;
+      for (int jx = 0; jx < 3; jx++) {
+        const Quat v = qmul(qc, qmul(qmul(qn, e[jx]), Rc));
+        d[55 + 0 * 3 + jx] = -c * s * v.x;
+        d[55 + 1 * 3 + jx] = -c * s * v.y;
+        d[55 + 2 * 3 + jx] = -c * s * v.z;
+      }
+    } else {
+#pragma unroll
+      for (int k = 55; k < 64; k++) d[k] = 0.0;
     }
-  } else {
-#pragma unroll
-    for (int k = 55; k < 64; k++) d[k] = 0.0;
+    if (has_prev) {
+      const Quat qp = load_q4(s_q + tid * 4);
+      const Quat Rp = load_q4(s_r + tid * 4);
+      const Quat pred = qmul(qp, Rp);                 // M_{i-1} q_{i-1}
+      const double s = sgn(qdot(pred, q));
+      ax += -c * s * pred.x; ay += -c * s * pred.y; az += -c * s * pred.z; aw += -c * s * pred.w;
+    }
+    const Quat a = {ax, ay, az, aw};
+    const Quat gq = qmul(qc, a);                      // Gq(q)^T a = vec(conj(q) (x) a)
+    const double beta = -qdot(q, a);
+    d[42] = rho;
+    d[43] = gq.x; d[44] = gq.y; d[45] = gq.z;
+    // beta I + hat(g)
+    d[46] = beta;  d[47] = -gq.z; d[48] = gq.y;
+    d[49] = gq.z;  d[50] = beta;  d[51] = -gq.x;
+    d[52] = -gq.y; d[53] = gq.x;  d[54] = beta;
   }
-  if (has_prev) {
-    const Quat qp = load_q(st + (f - 1) * 10);
-    const Quat Rp = load_q4(crot + (f - 1) * 4);
-    const Quat pred = qmul(qp, Rp);                 // M_{i-1} q_{i-1}
-    const double s = sgn(qdot(pred, q));
-    ax += -c * s * pred.x; ay += -c * s * pred.y; az += -c * s * pred.z; aw += -c * s * pred.w;
+  __syncthreads();
+  for (int i = tid; i < nf * 22; i += kQtFrames) {
+    const int lf = i / 22, e = i - lf * 22;
+    drec[(f0 + lf) * VS_DREC + 42 + e] = s_out[lf * kQtOut + e];
   }
-  const Quat a = {ax, ay, az, aw};
-  const Quat gq = qmul(qc, a);                      // Gq(q)^T a = vec(conj(q) (x) a)
-  const double beta = -qdot(q, a);
-  d[42] = rho;
-  d[43] = gq.x; d[44] = gq.y; d[45] = gq.z;
-  // beta I + hat(g)
-  d[46] = beta;  d[47] = -gq.z; d[48] = gq.y;
-  d[49] = gq.z;  d[50] = beta;  d[51] = -gq.x;
-  d[52] = -gq.y; d[53] = gq.x;  d[54] = beta;
 }
 
 int launch_quat_terms(vinsat_ctx* ctx, int64_t T, const double* st, const double* crot, const int32_t* gap,
@@ -278,6 +309,157 @@ int launch_orbit_propagate(vinsat_ctx* ctx, int64_t n_traj, int64_t n_steps, int
                            const double* x0, double* out) {
   if (n_traj == 0) return VINSAT_OK;
   VS_LAUNCH(ctx, F_SIM, k_orbit_propagate, ceil_div(n_traj, 128), 128, 0, n_traj, n_steps, stride, h, x0, out);
+  return VINSAT_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// Input preparation on the device
+// ---------------------------------------------------------------------------------------------------------
+// BA_utils.py:962-968: q <- clip(q/|q|, -1, 1); theta = 2 acos(w); log = xyz / sin(theta/2) * theta   (0/0 -> NaN, as torch)
+__device__ __forceinline__ void qlog(const Quat& q, double& lx, double& ly, double& lz) {
+  const double n = qnorm_exact(q);
+  auto clip = [](double v) { return v < -1.0 ? -1.0 : (v > 1.0 ? 1.0 : v); };
+  const double x = clip(q.x / n), y = clip(q.y / n), z = clip(q.z / n), w = clip(q.w / n);
+  const double theta = 2.0 * acos(w);
+  const double sh = sin(0.5 * theta);
+  lx = (x / sh) * theta; ly = (y / sh) * theta; lz = (z / sh) * theta;
+}
+
+// compute_omega_from_quat (BA_utils.py:1361-1367): omega_s = log(normalize(conj(q_s) (x) q_{s+1})) / dt, last row 0
+__global__ void __launch_bounds__(256) k_omega_from_quat(int64_t n, const double* __restrict__ quat, double dt,
+                                                         double* __restrict__ omega) {
+  const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  double ox = 0.0, oy = 0.0, oz = 0.0;
+  if (s + 1 < n) {
+    const Quat a = load_q4(quat + s * 4), b = load_q4(quat + (s + 1) * 4);
+    Quat dq = qmul_exact(qconj(a), b);
+    const double nn = qnorm_exact(dq);
+    dq.x /= nn; dq.y /= nn; dq.z /= nn; dq.w /= nn;
+    qlog(dq, ox, oy, oz);
+    ox /= dt; oy /= dt; oz /= dt;
+  }
+  omega[s * 3] = ox; omega[s * 3 + 1] = oy; omega[s * 3 + 2] = oz;
+}
+
+// precompute_cum_rotations (BA_utils.py:278-288) restricted to the slice `predict` reads (cum_rotations[:, :, -1],
+// :295): frame i gets the ordered product of exp(dt*omega_s), s = time_idx[i] .. time_idx[i+1]-1; the reference's
+// zero padding multiplies by the identity quaternion (exact), the last frame is the identity.
+__global__ void __launch_bounds__(128) k_cum_rot_frames(int64_t T, int64_t n_full, const int64_t* __restrict__ time_idx,
+                                                        const double* __restrict__ omega, double dt,
+                                                        double* __restrict__ cum_rot, int32_t* __restrict__ err) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  Quat c = {0.0, 0.0, 0.0, 1.0};
+  if (i + 1 < T) {
+    const int64_t s0 = time_idx[i], s1 = time_idx[i + 1];
+    if (s0 < 0 || s1 <= s0 || s1 > n_full) { atomicOr(err, 1); }
+    else {
+      for (int64_t s = s0; s < s1; s++) {
+        const Quat r = qexp(dt * omega[s * 3], dt * omega[s * 3 + 1], dt * omega[s * 3 + 2]);
+        c = (s == s0) ? r : qmul_exact(c, r);
+      }
+    }
+  }
+  cum_rot[i * 4] = c.x; cum_rot[i * 4 + 1] = c.y; cum_rot[i * 4 + 2] = c.z; cum_rot[i * 4 + 3] = c.w;
+}
+
+// the general form (all prefixes): omegas [T, N, 3] -> cum [T, N, 4]; one thread per frame
+__global__ void __launch_bounds__(128) k_cum_rot_prefix(int64_t T, int64_t N, const double* __restrict__ omegas,
+                                                        double dt, double* __restrict__ cum) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  Quat c = {0.0, 0.0, 0.0, 1.0};
+  for (int64_t j = 0; j < N; j++) {
+    const double* o = omegas + (i * N + j) * 3;
+    const Quat r = qexp(dt * o[0], dt * o[1], dt * o[2]);
+    c = (j == 0) ? r : qmul_exact(c, r);
+    double* d = cum + (i * N + j) * 4;
+    d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
+  }
+}
+
+int launch_omega_from_quat(vinsat_ctx* ctx, int64_t n, const double* quat, double dt, double* omega) {
+  if (n == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_SIM, k_omega_from_quat, ceil_div(n, 256), 256, 0, n, quat, dt, omega);
+  return VINSAT_OK;
+}
+int launch_cum_rot_frames(vinsat_ctx* ctx, int64_t T, int64_t n_full, const int64_t* time_idx, const double* omega,
+                          double dt, double* cum_rot, int32_t* err) {
+  if (T == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_SIM, k_cum_rot_frames, ceil_div(T, 128), 128, 0, T, n_full, time_idx, omega, dt, cum_rot, err);
+  return VINSAT_OK;
+}
+int launch_cum_rot_prefix(vinsat_ctx* ctx, int64_t T, int64_t N, const double* omegas, double dt, double* cum) {
+  if (T == 0 || N == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_SIM, k_cum_rot_prefix, ceil_div(T, 128), 128, 0, T, N, omegas, dt, cum);
+  return VINSAT_OK;
+}
+
+// Rigid-body attitude simulation (trajgen_pipe.py:155-207, scalar-FIRST quaternion [s, v], state [q, omega]):
+//   q_dot = 1/2 L(q) H omega,  omega_dot = -J^-1 (omega x J omega),  J = diag(jx, jy, jz) (trajgen_pipe.py:185),
+// classic RK4, then q normalised (:205).  attitude_dynamics normalises ITS ARGUMENT in place (:187): the stage
+// arguments are temporaries, but the first call normalises the step's own state before the later stages use it.
+struct Att { double s, x, y, z, wx, wy, wz; };
+__device__ __forceinline__ Att att_axpy(const Att& a, double h, const Att& f) {
+  return Att{a.s + h * f.s, a.x + h * f.x, a.y + h * f.y, a.z + h * f.z, a.wx + h * f.wx, a.wy + h * f.wy, a.wz + h * f.wz};
+}
+__device__ __forceinline__ Att att_dyn(Att& a, double jx, double jy, double jz) {
+  const double n = sqrt(a.s * a.s + a.x * a.x + a.y * a.y + a.z * a.z);
+  a.s /= n; a.x /= n; a.y /= n; a.z /= n;
+  Att f;
+  f.s = 0.5 * (-a.x * a.wx - a.y * a.wy - a.z * a.wz);
+  f.x = 0.5 * (a.s * a.wx - a.z * a.wy + a.y * a.wz);
+  f.y = 0.5 * (a.z * a.wx + a.s * a.wy - a.x * a.wz);
+  f.z = 0.5 * (-a.y * a.wx + a.x * a.wy + a.s * a.wz);
+  const double hx = jx * a.wx, hy = jy * a.wy, hz = jz * a.wz;      // J omega
+  f.wx = -(a.wy * hz - a.wz * hy) / jx;
+  f.wy = -(a.wz * hx - a.wx * hz) / jy;
+  f.wz = -(a.wx * hy - a.wy * hx) / jz;
+  return f;
+}
+
+__global__ void __launch_bounds__(128) k_attitude_propagate(int64_t n_traj, int64_t n_steps, int64_t stride, double h,
+                                                            double jx, double jy, double jz,
+                                                            const double* __restrict__ x0, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_traj) return;
+  const int64_t n_out = n_steps / stride + 1;
+  const double* a0 = x0 + i * 7;
+  Att a = {a0[0], a0[1], a0[2], a0[3], a0[4], a0[5], a0[6]};
+  double* o = out + i * n_out * 7;
+  for (int64_t s = 0;; s++) {
+    if (s % stride == 0) {
+      double* d = o + (s / stride) * 7;
+      d[0] = a.s; d[1] = a.x; d[2] = a.y; d[3] = a.z; d[4] = a.wx; d[5] = a.wy; d[6] = a.wz;
+    }
+    if (s == n_steps) break;
+    const Att f1 = att_dyn(a, jx, jy, jz);                 // normalises a (see above)
+    Att t = att_axpy(a, 0.5 * h, f1);
+    const Att f2 = att_dyn(t, jx, jy, jz);
+    t = att_axpy(a, 0.5 * h, f2);
+    const Att f3 = att_dyn(t, jx, jy, jz);
+    t = att_axpy(a, h, f3);
+    const Att f4 = att_dyn(t, jx, jy, jz);
+    const double h6 = h / 6.0;
+    a.s += h6 * (f1.s + 2 * f2.s + 2 * f3.s + f4.s);
+    a.x += h6 * (f1.x + 2 * f2.x + 2 * f3.x + f4.x);
+    a.y += h6 * (f1.y + 2 * f2.y + 2 * f3.y + f4.y);
+    a.z += h6 * (f1.z + 2 * f2.z + 2 * f3.z + f4.z);
+    a.wx += h6 * (f1.wx + 2 * f2.wx + 2 * f3.wx + f4.wx);
+    a.wy += h6 * (f1.wy + 2 * f2.wy + 2 * f3.wy + f4.wy);
+    a.wz += h6 * (f1.wz + 2 * f2.wz + 2 * f3.wz + f4.wz);
+    const double n = sqrt(a.s * a.s + a.x * a.x + a.y * a.y + a.z * a.z);
+    a.s /= n; a.x /= n; a.y /= n; a.z /= n;
+  }
+}
+
+int launch_attitude_propagate(vinsat_ctx* ctx, int64_t n_traj, int64_t n_steps, int64_t stride, double h,
+                              const double* inertia, const double* x0, double* out) {
+  if (n_traj == 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_SIM, k_attitude_propagate, ceil_div(n_traj, 128), 128, 0, n_traj, n_steps, stride, h, inertia[0],
+            inertia[1], inertia[2], x0, out);
   return VINSAT_OK;
 }
 

@@ -621,23 +621,35 @@ __global__ void __launch_bounds__(128) k_solve_init(int64_t T, const int32_t* __
   d[6] = 0.0; d[7] = 0.0; d[8] = 0.0;
 }
 
-// retraction (BA_filtering.py:56-60): p + dp, normalize(q (x) exp(dtheta)), v + dv; one thread per frame
+// retraction (BA_filtering.py:56-60): p + dp, normalize(q (x) exp(dtheta)), v + dv; one thread per frame, rows
+// staged through shared memory so that the 80 B / 72 B records move as coalesced runs
 __global__ void __launch_bounds__(128) k_retract(int64_t T, const int32_t* __restrict__ fprob,
                                                  const int32_t* __restrict__ active,
                                                  const double* __restrict__ st, const double* __restrict__ delta,
                                                  double* __restrict__ st_new) {
-  const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (f >= T) return;
-  if (!active[fprob[f]]) return;
-  const double* s = st + f * 10;
-  const double* d = delta + f * 9;
-  double* o = st_new + f * 10;
-  o[0] = s[0] + d[0]; o[1] = s[1] + d[1]; o[2] = s[2] + d[2];
-  o[7] = s[7] + d[6]; o[8] = s[8] + d[7]; o[9] = s[9] + d[8];
-  const Quat q = {s[3], s[4], s[5], s[6]};
-  const Quat n = qmul(q, qexp(d[3], d[4], d[5]));
-  const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z + n.w * n.w);
-  o[3] = n.x / nn; o[4] = n.y / nn; o[5] = n.z / nn; o[6] = n.w / nn;
+  __shared__ double s_st[128 * 10 + 1];
+  __shared__ double s_d[128 * 9];
+  __shared__ int s_act[128];
+  const int tid = threadIdx.x;
+  const int64_t f0 = (int64_t)blockIdx.x * 128;
+  const int nf = (int)min((int64_t)128, T - f0);
+  s_act[tid] = (tid < nf) ? active[fprob[f0 + tid]] : 0;
+  for (int i = tid; i < nf * 10; i += 128) s_st[i] = st[f0 * 10 + i];
+  for (int i = tid; i < nf * 9; i += 128) s_d[i] = delta[f0 * 9 + i];
+  __syncthreads();
+  if (tid < nf && s_act[tid]) {
+    double* s = s_st + tid * 10;
+    const double* d = s_d + tid * 9;
+    const Quat q = {s[3], s[4], s[5], s[6]};
+    const Quat n = qmul(q, qexp(d[3], d[4], d[5]));
+    const double nn = sqrt(n.x * n.x + n.y * n.y + n.z * n.z + n.w * n.w);
+    s[0] += d[0]; s[1] += d[1]; s[2] += d[2];
+    s[7] += d[6]; s[8] += d[7]; s[9] += d[8];
+    s[3] = n.x / nn; s[4] = n.y / nn; s[5] = n.z / nn; s[6] = n.w / nn;
+  }
+  __syncthreads();
+  for (int i = tid; i < nf * 10; i += 128)
+    if (s_act[i / 10]) st_new[f0 * 10 + i] = s_st[i];
 }
 
 int launch_solve_init_only(vinsat_batch* b) {

@@ -59,4 +59,12 @@ int launch_seg_backsub(vinsat_batch* b);                                    // i
 int launch_reduced_packed(vinsat_batch* b, int64_t S_total, const double* pack, double* rsys, double* rlow,
                           double* rwrec, double* xsep, const int32_t* one_chain /* {0, S_total, 0} on device */);
 
+// ---- input preparation / simulation (kernels_dyn.cu) --------------------------------------------------
+int launch_omega_from_quat(vinsat_ctx* ctx, int64_t n, const double* quat, double dt, double* omega);
+int launch_cum_rot_frames(vinsat_ctx* ctx, int64_t T, int64_t n_full, const int64_t* time_idx, const double* omega,
+                          double dt, double* cum_rot, int32_t* err);
+int launch_cum_rot_prefix(vinsat_ctx* ctx, int64_t T, int64_t N, const double* omegas, double dt, double* cum);
+int launch_attitude_propagate(vinsat_ctx* ctx, int64_t n_traj, int64_t n_steps, int64_t stride, double h,
+                              const double* inertia, const double* x0, double* out);
+
 }  // namespace vs

@@ -187,4 +187,64 @@ int vinsat_orbit_propagate(vinsat_ctx* ctx, int mem, int64_t n_traj, int64_t n_s
   return VINSAT_OK;
 }
 
+int vinsat_cum_rotations(vinsat_ctx* ctx, int mem, int64_t n_full, const double* quat_full, double dt,
+                         int64_t n_frames, const int64_t* time_idx, double* omega_out, double* cum_rot_out) {
+  VS_CHECK_ARG(ctx, ctx != nullptr);
+  VS_CHECK_ARG(ctx, n_full >= 0 && n_frames >= 0 && dt != 0.0 && (n_full == 0 || quat_full));
+  VS_CHECK_ARG(ctx, n_frames == 0 || (time_idx && cum_rot_out));
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  InBuf<double> q;
+  InBuf<int64_t> ti;
+  OutBuf<double> om, cr;
+  DevBuf<double> om_own;
+  DevBuf<int32_t> err;
+  VS_TRY(q.init(ctx, mem, quat_full, n_full * 4));
+  VS_TRY(ti.init(ctx, mem, time_idx, n_frames));
+  VS_TRY(om.init(ctx, mem, omega_out, n_full * 3));
+  VS_TRY(cr.init(ctx, mem, cum_rot_out, n_frames * 4));
+  double* omega = om.p;
+  if (!omega) { VS_CUDA(ctx, om_own.alloc(n_full * 3)); omega = om_own.p; }
+  VS_CUDA(ctx, err.alloc(1));
+  VS_CUDA(ctx, cudaMemsetAsync(err.p, 0, sizeof(int32_t), ctx->stream));
+  VS_TRY(launch_omega_from_quat(ctx, n_full, q.p, dt, omega));
+  VS_TRY(launch_cum_rot_frames(ctx, n_frames, n_full, ti.p, omega, dt, cr.p, err.p));
+  VS_TRY(om.finish(ctx)); VS_TRY(cr.finish(ctx));
+  int32_t h_err = 0;
+  VS_CUDA(ctx, cudaMemcpyAsync(&h_err, err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_err) return set_error(ctx, VINSAT_EINVAL, "cum_rotations: time_idx must be strictly increasing and < n_full");
+  return VINSAT_OK;
+}
+
+int vinsat_precompute_cum_rotations(vinsat_ctx* ctx, int mem, int64_t n_frames, int64_t n_slots, const double* omegas,
+                                    double dt, double* cum_out) {
+  VS_CHECK_ARG(ctx, ctx != nullptr);
+  VS_CHECK_ARG(ctx, n_frames >= 0 && n_slots >= 0 && (n_frames * n_slots == 0 || (omegas && cum_out)));
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  InBuf<double> in;
+  OutBuf<double> o;
+  VS_TRY(in.init(ctx, mem, omegas, n_frames * n_slots * 3));
+  VS_TRY(o.init(ctx, mem, cum_out, n_frames * n_slots * 4));
+  VS_TRY(launch_cum_rot_prefix(ctx, n_frames, n_slots, in.p, dt, o.p));
+  VS_TRY(o.finish(ctx));
+  VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VINSAT_OK;
+}
+
+int vinsat_attitude_propagate(vinsat_ctx* ctx, int mem, int64_t n_traj, int64_t n_steps, int64_t stride, double h,
+                              const double* inertia_diag, const double* x0, double* out) {
+  VS_CHECK_ARG(ctx, ctx != nullptr);
+  VS_CHECK_ARG(ctx, n_traj >= 0 && n_steps >= 0 && stride >= 1 && inertia_diag && x0 && out);
+  VS_CHECK_ARG(ctx, inertia_diag[0] > 0 && inertia_diag[1] > 0 && inertia_diag[2] > 0);
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  InBuf<double> in;
+  OutBuf<double> o;
+  VS_TRY(in.init(ctx, mem, x0, n_traj * 7));
+  VS_TRY(o.init(ctx, mem, out, n_traj * (n_steps / stride + 1) * 7));
+  VS_TRY(launch_attitude_propagate(ctx, n_traj, n_steps, stride, h, inertia_diag, in.p, o.p));
+  VS_TRY(o.finish(ctx));
+  VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VINSAT_OK;
+}
+
 }  // extern "C"

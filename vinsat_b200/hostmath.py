@@ -54,6 +54,15 @@ def compute_omega_from_quat(quat, dt):
     return np.concatenate([quaternion_log(dq) / dt, np.zeros((1, 3))], axis=0)
 
 
+def precompute_cum_rotations(omegas, dt):
+    """BA/BA_utils.py:278-288 on the host: (..., N, 3) -> (..., N, 4) cumulative rotations along axis -2."""
+    rot = quaternion_exp(dt * np.asarray(omegas, dtype=np.float64))
+    out = [rot[..., 0, :]]
+    for i in range(1, rot.shape[-2]):
+        out.append(quaternion_multiply(out[-1], rot[..., i, :]))
+    return np.stack(out, axis=-2)
+
+
 def compute_velocity_from_pos(pos, dt):
     """BA/BA_utils.py:1370-1373 (forward difference, zero last row)."""
     return np.concatenate([(pos[1:] - pos[:-1]) / dt, np.zeros((1, 3))], axis=0)

@@ -15,7 +15,7 @@ from . import _lib, config
 from . import hostmath as hm
 from .BA.BA_filtering import BA  # noqa: F401  (same import surface as the reference)
 from .BA.BA_utils import (landmark_project, propagate_dynamics_init, quaternion_exp, quaternion_log,
-                          precompute_cum_rotations, compute_omega_from_quat, _ctx)
+                          precompute_cum_rotations, compute_omega_from_quat, cum_rotations_from_quat, _ctx)
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 
@@ -177,12 +177,10 @@ def streaming_version(detections=None, orbit_np=None, orbit_file_name=None, dete
     # initial guess (od_pipe.py:941-973); the torch RNG call order is the reference's
     T = len(gt_pos_eci)
     N = max(time_idx[1:] - time_idx[:-1])
-    gt_omega = compute_omega_from_quat(gt_quat_eci_full, dt)
     velocities = gt_vel_eci[time_idx].unsqueeze(0).double()
-    omegas = torch.zeros((1, T, N, 3)).double()
-    for i in range(1, T):
-        omegas[:, i - 1, :time_idx[i] - time_idx[i - 1], :] = gt_omega[time_idx[i - 1]:time_idx[i], :].unsqueeze(0).double()
-    cum_rot = precompute_cum_rotations(omegas, dt)[0, :, -1].numpy()      # the only slice `predict` reads
+    # od_pipe.py:944-953 (compute_omega_from_quat, zero-padded omegas (1,T,N,3), precompute_cum_rotations) as one
+    # device call that returns the only slice `predict` reads, cum_rotations[0, :, -1]
+    cum_rot, gt_omega = cum_rotations_from_quat(gt_quat_eci_full, time_idx, dt)
     position_offset = torch.randn((T, 3)) * 100
     orientation_offset = torch.randn([T, 3]) * 0.2
     velocity_offset = torch.randn([T, 3]) * velocities.abs().mean() * 0.1

@@ -80,6 +80,11 @@ def attitude_step(xk, h):                                       # :198-207
     return xn
 
 
+def propagate_attitudes(x0, n_steps, h=1.0, stride=1):
+    """Batched `for k: x = attitude_step(x, h)` on the device: x0 (n,7) -> (n, n_steps/stride+1, 7)."""
+    return _lib.default_context(config.device).attitude_propagate(x0, n_steps, stride, h)
+
+
 def generate_new_traj(orbit_type='polar', strict=False):
     """:209-251.  The reference draws random elements (:218/:222), simulates 3 h at 1 Hz and then FAILS at its
     `return` (it concatenates a 6xN and a 7xN array on axis 1).  With strict=True that ValueError
@@ -100,10 +105,7 @@ def generate_new_traj(orbit_type='polar', strict=False):
     q0 = np.ones(4) * 0.5
     q0 /= np.linalg.norm(q0)
     omega0 = 2 * (np.pi / 180) * np.ones(3) * 0.5
-    xtraj_attitude = np.zeros((7, len(tsamp)))
-    xtraj_attitude[:, 0] = np.hstack((q0, omega0))
-    for k in range(len(tsamp) - 1):
-        xtraj_attitude[:, k + 1] = attitude_step(xtraj_attitude[:, k].copy(), 1.0)
+    xtraj_attitude = propagate_attitudes(np.hstack((q0, omega0))[None], len(tsamp) - 1, 1.0)[0].T   # (7, N), device
     if strict:
         return np.concatenate([xtraj_orbit, xtraj_attitude], axis=1), tsamp          # raises ValueError (:251)
     return np.concatenate([xtraj_orbit, xtraj_attitude], axis=0), tsamp
