@@ -300,14 +300,23 @@ def run_gpu(args):
         for k in kern:
             kern[k]["frac"] = kern[k]["achieved"] / kern[k]["peak"]
             kern[k]["ms_per_launch"] = per_launch.get(k)
+        traffic, traffic_src = {}, None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp) and (P, T, K) == (1024, 1000, 10):        # captured on exactly this workload
+            tj = json.load(open(tp))
+            traffic = {k: v["dram_bytes_per_launch"] for k, v in tj["families"].items()}
+            traffic_src = tj["source"]
         rj_bytes = BYTES_PER_OBS_RESJAC * batch.M + BYTES_PER_FRAME_STATE * n_frames
-        rj_roof = dict(bound="hbm", achieved=rj_bytes / (rj_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s", traffic=None,
+        rj_roof = dict(bound="hbm", achieved=rj_bytes / (rj_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s",
+                       traffic=traffic.get("project_resjac"),
                        ms_per_launch=rj_ms, bytes_per_launch=rj_bytes)
         rj_roof["frac"] = rj_roof["achieved"] / hbm_peak
+        for k in kern:
+            kern[k]["traffic"] = traffic.get(k)
         dk = kern.get(dom, kern["blocktridiag_solve"])
         roofline = dict(kernel=dom if dom in kern else "blocktridiag_solve", bound=dk["bound"],
-                        achieved=dk["achieved"], peak=dk["peak"], unit=dk["unit"], frac=dk["frac"], traffic=None,
-                        peak_source=peak_src, share_of_step=fam_ms.get(dom, 0) / tot_ms)
+                        achieved=dk["achieved"], peak=dk["peak"], unit=dk["unit"], frac=dk["frac"],
+                        traffic=dk.get("traffic"), traffic_source=traffic_src, peak_source=peak_src, share_of_step=fam_ms.get(dom, 0) / tot_ms)
         cb = None
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
