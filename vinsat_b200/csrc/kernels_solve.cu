@@ -467,8 +467,28 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Sum over the kPT threads that share a problem: one warp (kPT = 32, several problems per CTA) or the whole CTA
+// (kPT = blockDim.x = 1024, one problem per CTA: a 100 000-frame arc summed by one warp took 1.9 ms per call).
+// Fixed shape => deterministic.  Result valid in the group's first thread.
+template <int kPT>
+__device__ __forceinline__ double group_total(double v, double* s_part) {
+  v = warp_sum(v);
+  if (kPT == 32) return v;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();                       // s_part may still be read from the previous call
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {
+    t = (lane < kPT / 32) ? s_part[lane] : 0.0;
+    t = warp_sum(t);
+  }
+  return t;
+}
+
 // init_residual = mean |[r_obs ; sqrt(Sigma) r_pred]| (BA_filtering.py:51); also arms the LM loop.
-__global__ void __launch_bounds__(128) k_init_residual(int P, const int64_t* __restrict__ frame_off,
+template <int kPT>
+__global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_init_residual(int P, const int64_t* __restrict__ frame_off,
                                                        const int64_t* __restrict__ obs_off,
                                                        const int32_t* __restrict__ gap,
                                                        const double* __restrict__ grec,
@@ -476,20 +496,21 @@ __global__ void __launch_bounds__(128) k_init_residual(int P, const int64_t* __r
                                                        double sqrt_sigma, const double* __restrict__ lam_in,
                                                        double* __restrict__ lam, double* __restrict__ init_res,
                                                        int32_t* __restrict__ active, int32_t* __restrict__ ntrials) {
-  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (p >= P) return;
+  __shared__ double s_part[32];
+  const int p = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kPT);
+  const int lane = threadIdx.x % kPT;
+  if (p >= P) return;                    // whole groups leave together (kPT divides blockDim.x)
   const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
   double so = 0.0, sd = 0.0;
-  for (int64_t f = f0 + lane; f < f1; f += 32) {
+  for (int64_t f = f0 + lane; f < f1; f += kPT) {
     so += grec[f * VS_GREC + 27];
     if (!initialize && gap[f] > 0) {
       const double* d = drec + f * VS_DREC + 36;
       sd += fabs(d[0]) + fabs(d[1]) + fabs(d[2]) + fabs(d[3]) + fabs(d[4]) + fabs(d[5]) + fabs(d[6]);
     }
   }
-  so = warp_sum(so);
-  sd = warp_sum(sd);
+  so = group_total<kPT>(so, s_part);
+  sd = group_total<kPT>(sd, s_part);
   if (lane == 0) {
     const double n = 2.0 * (double)(obs_off[p + 1] - obs_off[p]) + (initialize ? 6.0 : 7.0) * (double)max((long long)(f1 - f0 - 1), 0ll);
     init_res[p] = (so + sqrt_sigma * sd) / n;
@@ -502,14 +523,21 @@ __global__ void __launch_bounds__(128) k_init_residual(int P, const int64_t* __r
 int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double, const double* d_lam_in) {
   vinsat_ctx* ctx = b->ctx;
   if (b->P == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_ACCEPT, k_init_residual, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off,
-            b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
-            b->active, b->ntrials);
+  if (b->T > 4096 * b->P) {              // long arcs: one CTA per problem
+    VS_LAUNCH(ctx, F_ACCEPT, k_init_residual<1024>, (unsigned)b->P, 1024, 0, (int)b->P, b->d_frame_off,
+              b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
+              b->active, b->ntrials);
+  } else {
+    VS_LAUNCH(ctx, F_ACCEPT, k_init_residual<32>, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off,
+              b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
+              b->active, b->ntrials);
+  }
   return VINSAT_OK;
 }
 
 // accept test (BA_filtering.py:66-79)
-__global__ void __launch_bounds__(128) k_accept(int P, const int64_t* __restrict__ frame_off,
+template <int kPT>
+__global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_accept(int P, const int64_t* __restrict__ frame_off,
                                                 const int64_t* __restrict__ obs_off,
                                                 const unsigned long long* __restrict__ wmax,
                                                 const double* __restrict__ e_obs, const double* __restrict__ e_dyn,
@@ -517,18 +545,19 @@ __global__ void __launch_bounds__(128) k_accept(int P, const int64_t* __restrict
                                                 const double* __restrict__ init_res, double* __restrict__ lam,
                                                 double* __restrict__ lam_next, int32_t* __restrict__ active,
                                                 int32_t* __restrict__ ntrials, int32_t* __restrict__ flags) {
-  const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  __shared__ double s_part[32];
+  const int p = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kPT);
+  const int lane = threadIdx.x % kPT;
   if (p >= P) return;
-  if (!active[p]) return;
+  if (!active[p]) return;                // uniform over the group
   const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
   double so = 0.0, sd = 0.0;
-  for (int64_t f = f0 + lane; f < f1; f += 32) {
+  for (int64_t f = f0 + lane; f < f1; f += kPT) {
     so += e_obs[f];
     if (!initialize && f + 1 < f1) sd += e_dyn[f];
   }
-  so = warp_sum(so);
-  sd = warp_sum(sd);
+  so = group_total<kPT>(so, s_part);
+  sd = group_total<kPT>(sd, s_part);
   if (lane == 0) {
     const unsigned long long wb = wmax[p];
     const double invw = wb ? 1.0 / __longlong_as_double((long long)wb) : 0.0;
@@ -550,9 +579,15 @@ __global__ void __launch_bounds__(128) k_accept(int P, const int64_t* __restrict
 int launch_accept(vinsat_batch* b, int initialize, double Sigma) {
   vinsat_ctx* ctx = b->ctx;
   if (b->P == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_ACCEPT, k_accept, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
-            b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
-            b->ntrials, b->flags);
+  if (b->T > 4096 * b->P) {
+    VS_LAUNCH(ctx, F_ACCEPT, k_accept<1024>, (unsigned)b->P, 1024, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
+              b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
+              b->ntrials, b->flags);
+  } else {
+    VS_LAUNCH(ctx, F_ACCEPT, k_accept<32>, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
+              b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
+              b->ntrials, b->flags);
+  }
   return VINSAT_OK;
 }
 
