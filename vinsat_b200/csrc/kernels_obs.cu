@@ -607,6 +607,188 @@ __global__ void __launch_bounds__(kStageThreads, kMinBlocks) k_obs_assemble_stag
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Two-pass variant (default).  The walk above is one long dependent chain per observation (division, two rsqrt,
+// ~40 dependent FP64 operations) repeated sequentially for a frame's observations: time = observations x chain
+// latency / resident threads, and the 27 accumulators cap the resident threads at 12 warps per SM.  Here ONE WARP
+// owns 32 consecutive frames and splits the work by what is parallel in it:
+//   pass 1  one lane per OBSERVATION of the tile (independent iterations, no loop-carried state): camera-frame
+//           point, reciprocal depth, residual, robust weight -> written back over the staged inputs in shared memory
+//   pass 2  one lane per FRAME: only the products and the 27 accumulations remain (dependency depth ~6, 27
+//           independent chains), reading the per-observation basics from shared memory
+// The per-frame constants pass 1 needs (rotation, position, intrinsics, 1/c, 1/c^2) go through a small shared table.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int k2pChunk = 320;                 // observations per chunk (32 frames x 10; more obs => more chunks)
+constexpr int k2pSlots = 7;                   // Xc Yc Zc | ru rv | w | d    (staged as X0 X1 X2 | u v | conf | -)
+constexpr int k2pFrameRec = 19;               // Rt 9 | p 3 | fx fy cx cy | 1/c | 1/c^2 | (pad: odd pitch)
+
+__global__ void __launch_bounds__(32, 9) k_obs_assemble_2pass(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
+                                                              const int32_t* __restrict__ oframe,
+                                                              const int32_t* __restrict__ fprob,
+                                                              const double* __restrict__ X, const double* __restrict__ uv,
+                                                              const double* __restrict__ conf,
+                                                              const double* __restrict__ st,
+                                                              const double* __restrict__ intr,
+                                                              const double* __restrict__ c_obs, WeightParams wp,
+                                                              double* __restrict__ wu_out, double* __restrict__ grec,
+                                                              unsigned long long* __restrict__ wmax) {
+  extern __shared__ __align__(16) double sm2[];
+  double* tile = sm2;                                       // [k2pSlots][k2pChunk]
+  double* fdat = sm2 + k2pSlots * k2pChunk;                 // [32][k2pFrameRec]
+  int32_t* ofr = reinterpret_cast<int32_t*>(fdat + 32 * k2pFrameRec);     // [k2pChunk] frame of each staged observation
+  const int lane = threadIdx.x;
+  const int64_t f0 = (int64_t)blockIdx.x * 32;
+  const int64_t f = f0 + lane;
+  const bool valid = f < T;
+  const int kb = obs_start[f0];
+  const int ke = obs_start[min(f0 + 32, T)];
+  auto issue_chunk = [&](int base) {
+    const int n = min(k2pChunk, ke - base);
+    for (int i = lane; i < n; i += 32) {
+      const int k = base + i;
+      __pipeline_memcpy_async(&tile[i], &X[k], 8);
+      __pipeline_memcpy_async(&tile[k2pChunk + i], &X[M + k], 8);
+      __pipeline_memcpy_async(&tile[2 * k2pChunk + i], &X[2 * M + k], 8);
+      __pipeline_memcpy_async(&tile[3 * k2pChunk + i], &uv[k], 8);
+      __pipeline_memcpy_async(&tile[4 * k2pChunk + i], &uv[M + k], 8);
+      __pipeline_memcpy_async(&tile[5 * k2pChunk + i], &conf[k], 8);
+      __pipeline_memcpy_async(&ofr[i], &oframe[k], 4);
+    }
+    __pipeline_commit();
+  };
+  issue_chunk(kb);
+  int k0 = 0, k1 = 0, p = 0;
+  double Rt[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rt[i] = 0.0;
+  double4 ci = make_double4(0, 0, 0, 0);
+  {
+    double* fd = fdat + lane * k2pFrameRec;
+    double px = 0, py = 0, pz = 0;
+    FrameWeight fw = {1.0, 1.0, 1.0};
+    if (valid) {
+      k0 = obs_start[f]; k1 = obs_start[f + 1];
+      p = fprob[f];
+      if (k1 > k0) {
+        fw = frame_weight(c_obs[p], wp);
+        const double* s = st + f * 10;
+        ci = *reinterpret_cast<const double4*>(intr + f * 4);
+        px = s[0]; py = s[1]; pz = s[2];
+        const double qn = 1.0 / sqrt(s[3] * s[3] + s[4] * s[4] + s[5] * s[5] + s[6] * s[6]);
+        const double x = s[3] * qn, y = s[4] * qn, z = s[5] * qn, w = s[6] * qn;
+        Rt[0] = 1 - 2 * (y * y + z * z); Rt[1] = 2 * (x * y + z * w);     Rt[2] = 2 * (x * z - y * w);
+        Rt[3] = 2 * (x * y - z * w);     Rt[4] = 1 - 2 * (x * x + z * z); Rt[5] = 2 * (y * z + x * w);
+        Rt[6] = 2 * (x * z + y * w);     Rt[7] = 2 * (y * z - x * w);     Rt[8] = 1 - 2 * (x * x + y * y);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) fd[i] = Rt[i];
+    fd[9] = px; fd[10] = py; fd[11] = pz;
+    fd[12] = ci.x; fd[13] = ci.y; fd[14] = ci.z; fd[15] = ci.w;
+    fd[16] = fw.inv_c; fd[17] = fw.inv_c2;
+  }
+  // the tile's frames usually belong to one problem: then the largest raw weight is reduced in registers
+  const int p_first = __shfl_sync(0xffffffffu, p, 0);
+  const bool one_problem = __all_sync(0xffffffffu, !valid || p == p_first);
+  const double inv_am2 = wp.alpha_is_two ? 0.0 : 1.0 / wp.am2;
+  double sN[5] = {0, 0, 0, 0, 0}, sNH[9], sHNH[6] = {0, 0, 0, 0, 0, 0}, sm[3] = {0, 0, 0}, sHm[3] = {0, 0, 0}, sabs = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) sNH[i] = 0.0;
+  double wloc = 0.0;
+  for (int base = kb; base < ke; base += k2pChunk) {
+    const int n = min(k2pChunk, ke - base);
+    __pipeline_wait_prior(0);
+    __syncwarp();
+    // ---- pass 1: one lane per observation
+#pragma unroll 2
+    for (int i = lane; i < n; i += 32) {
+      const int lf = ofr[i] - (int)f0;
+      const double* fd = fdat + lf * k2pFrameRec;
+      const double dx = tile[i] - fd[9], dy = tile[k2pChunk + i] - fd[10], dz = tile[2 * k2pChunk + i] - fd[11];
+      const double Xc = fd[0] * dx + fd[1] * dy + fd[2] * dz;
+      const double Yc = fd[3] * dx + fd[4] * dy + fd[5] * dz;
+      const double Zc = fd[6] * dx + fd[7] * dy + fd[8] * dz;
+      const double d = 1.0 / fmax(Zc, 0.1);
+      const double a = fd[12] * d, bb = fd[13] * d;
+      const double ru = tile[3 * k2pChunk + i] - (a * Xc + fd[14]), rv = tile[4 * k2pChunk + i] - (bb * Yc + fd[15]);
+      FrameWeight fw; fw.inv_c = fd[16]; fw.inv_am2 = inv_am2; fw.inv_c2 = fd[17];
+      const double wraw = 0.5 * (robust_component_fast(ru, fw, wp) + robust_component_fast(rv, fw, wp));
+      const double w = wraw * tile[5 * k2pChunk + i];
+      tile[i] = Xc; tile[k2pChunk + i] = Yc; tile[2 * k2pChunk + i] = Zc;
+      tile[3 * k2pChunk + i] = ru; tile[4 * k2pChunk + i] = rv;
+      tile[5 * k2pChunk + i] = w;
+      tile[6 * k2pChunk + i] = d;
+      if (one_problem) wloc = fmax(wloc, wraw);
+      else if (wraw > 0.0) atomicMax(&wmax[fprob[f0 + lf]], (unsigned long long)__double_as_longlong(wraw));
+    }
+    __syncwarp();
+    // ---- pass 2: one lane per frame
+    const int lo = max(k0, base), hi = min(k1, base + n);
+    for (int k = lo; k < hi; k++) {
+      const int i = k - base;
+      const double Xc = tile[i], Yc = tile[k2pChunk + i], Zc = tile[2 * k2pChunk + i];
+      const double ru = tile[3 * k2pChunk + i], rv = tile[4 * k2pChunk + i];
+      const double w = tile[5 * k2pChunk + i], d = tile[6 * k2pChunk + i];
+      const double live = (Zc >= 0.1) ? 1.0 : 0.0;
+      const double a = ci.x * d, bb = ci.y * d;
+      const double cc = -a * Xc * d * live, ee = -bb * Yc * d * live;
+      sabs += fabs(ru) + fabs(rv);
+      const double wa = w * a, wb = w * bb;
+      const double n00 = wa * a, n02 = wa * cc, n11 = wb * bb, n12 = wb * ee, n22 = w * (cc * cc + ee * ee);
+      sN[0] += n00; sN[1] += n02; sN[2] += n11; sN[3] += n12; sN[4] += n22;
+      const double h00 = -n02 * Yc, h01 = n02 * Xc - n00 * Zc, h02 = n00 * Yc;
+      const double h10 = n11 * Zc - n12 * Yc, h11 = n12 * Xc, h12 = -n11 * Xc;
+      const double h20 = n12 * Zc - n22 * Yc, h21 = n22 * Xc - n02 * Zc, h22 = n02 * Yc - n12 * Xc;
+      sNH[0] += h00; sNH[1] += h01; sNH[2] += h02; sNH[3] += h10; sNH[4] += h11; sNH[5] += h12;
+      sNH[6] += h20; sNH[7] += h21; sNH[8] += h22;
+      sHNH[0] += Zc * h10 - Yc * h20; sHNH[1] += Zc * h11 - Yc * h21; sHNH[2] += Zc * h12 - Yc * h22;
+      sHNH[3] += Xc * h21 - Zc * h01; sHNH[4] += Xc * h22 - Zc * h02; sHNH[5] += Yc * h02 - Xc * h12;
+      const double m0 = wa * ru, m1 = wb * rv, m2 = w * (cc * ru + ee * rv);
+      sm[0] += m0; sm[1] += m1; sm[2] += m2;
+      sHm[0] += Zc * m1 - Yc * m2; sHm[1] += Xc * m2 - Zc * m0; sHm[2] += Yc * m0 - Xc * m1;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) wu_out[base + i] = tile[5 * k2pChunk + i];
+    __syncwarp();
+    if (base + k2pChunk < ke) issue_chunk(base + k2pChunk);
+  }
+  if (one_problem) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wloc = fmax(wloc, __shfl_xor_sync(0xffffffffu, wloc, o));
+    if (lane == 0 && wloc > 0.0) atomicMax(&wmax[p_first], (unsigned long long)__double_as_longlong(wloc));
+  }
+  if (valid) {
+    const double N[9] = {sN[0], 0.0, sN[1], 0.0, sN[2], sN[3], sN[1], sN[3], sN[4]};
+    double NR[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) NR[i * 3 + j] = N[i * 3] * Rt[j] + N[i * 3 + 1] * Rt[3 + j] + N[i * 3 + 2] * Rt[6 + j];
+    double out[VS_GREC];
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+      for (int bcol = a; bcol < 3; bcol++)
+        out[idx++] = Rt[a] * NR[bcol] + Rt[3 + a] * NR[3 + bcol] + Rt[6 + a] * NR[6 + bcol];
+#pragma unroll
+      for (int bcol = 0; bcol < 3; bcol++)
+        out[idx++] = -2.0 * (Rt[a] * sNH[bcol] + Rt[3 + a] * sNH[3 + bcol] + Rt[6 + a] * sNH[6 + bcol]);
+    }
+    out[idx++] = 4.0 * sHNH[0]; out[idx++] = 4.0 * sHNH[1]; out[idx++] = 4.0 * sHNH[2];
+    out[idx++] = 4.0 * sHNH[3]; out[idx++] = 4.0 * sHNH[4];
+    out[idx++] = 4.0 * sHNH[5];
+#pragma unroll
+    for (int a = 0; a < 3; a++) out[21 + a] = -(Rt[a] * sm[0] + Rt[3 + a] * sm[1] + Rt[6 + a] * sm[2]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) out[24 + a] = 2.0 * sHm[a];
+    out[27] = sabs;
+    double* g = grec + f * VS_GREC;
+#pragma unroll
+    for (int i = 0; i < VS_GREC; i += 2) *reinterpret_cast<double2*>(g + i) = make_double2(out[i], out[i + 1]);
+  }
+}
+
 int launch_obs_assemble(vinsat_batch* b, double alpha) {
   vinsat_ctx* ctx = b->ctx;
   WeightParams wp;
@@ -640,7 +822,18 @@ int launch_obs_assemble(vinsat_batch* b, double alpha) {
   } while (0)
   if (variant == 30) STAGED_LAUNCH(128, 1408, 1, 3);     // 67.6 KB, 3 CTAs per SM
   if (variant == 31) STAGED_LAUNCH(64, 704, 1, 6);       // 33.8 KB, 6 CTAs per SM
-  if (variant == 0 || variant == 32) STAGED_LAUNCH(32, 352, 1, 12);      // default: one warp per CTA, 16.9 KB, 12 CTAs per SM
+  if (variant == 0 || variant == 50) {
+    static bool attr_set = false;
+    const int smem = (k2pSlots * k2pChunk + 32 * k2pFrameRec) * (int)sizeof(double) + k2pChunk * (int)sizeof(int32_t);
+    if (!attr_set) {
+      VS_CUDA(ctx, cudaFuncSetAttribute(k_obs_assemble_2pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_set = true;
+    }
+    VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_2pass, ceil_div(b->T, 32), 32, smem, b->T, b->M, b->obs_start, b->oframe,
+              b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
+    return VINSAT_OK;
+  }
+  if (variant == 32) STAGED_LAUNCH(32, 352, 1, 12);      // default: one warp per CTA, 16.9 KB, 12 CTAs per SM
   if (variant == 33) STAGED_LAUNCH(32, 352, 2, 12);
   if (variant == 34) STAGED_LAUNCH(32, 352, 2, 8);
   if (variant == 35) STAGED_LAUNCH(32, 352, 1, 16);
