@@ -147,10 +147,33 @@ __device__ __forceinline__ void accel_grad(double x, double y, double z, double&
   g[6] = xz * cza;       g[7] = yz * czb;       g[8] = z2 * czb + dz;
 }
 
+// Same acceleration with the arithmetic of accel_grad (one rsqrt, no division, no square root): used by the LM
+// trial residual, whose trajectory then follows the one the Jacobian kernel integrates.
+__device__ __forceinline__ void accel_fast(double x, double y, double z, double& ax, double& ay, double& az) {
+  const double x2 = x * x, y2 = y * y, z2 = z * z;
+  const double n2 = x2 + y2 + z2;
+  const double inv_n = rsqrt(n2);
+  const double inv_n2 = inv_n * inv_n;
+  const double inv_n3 = inv_n * inv_n2;
+  const double inv_n7 = inv_n3 * inv_n2 * inv_n2;
+  const double k = -kMu * inv_n3, j = kJ2 * inv_n7;
+  const double sx = 6.0 * x2 - 1.5 * y2 - 1.5 * z2;
+  const double sz = 3.0 * x2 - 4.5 * y2 - 4.5 * z2;
+  const double dxy = k + j * sx, dz = k + j * sz;
+  ax = dxy * x;
+  ay = dxy * y;
+  az = dz * z;
+}
+
 // One classic RK4 step of the 6-state (BA_utils.py:901-912).
+template <bool FAST = false>
 __device__ __forceinline__ void rk4_step(double* x, double h) {
   double a1x, a1y, a1z, a2x, a2y, a2z, a3x, a3y, a3z, a4x, a4y, a4z;
   const double hh = 0.5 * h;
+  auto accel = [](double px, double py, double pz, double& ox, double& oy, double& oz) {
+    if (FAST) accel_fast(px, py, pz, ox, oy, oz);
+    else vs::accel(px, py, pz, ox, oy, oz);
+  };
   accel(x[0], x[1], x[2], a1x, a1y, a1z);
   double p2x = x[0] + hh * x[3], p2y = x[1] + hh * x[4], p2z = x[2] + hh * x[5];
   double v2x = x[3] + hh * a1x, v2y = x[4] + hh * a1y, v2z = x[5] + hh * a1z;

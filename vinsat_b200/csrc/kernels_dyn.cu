@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128) k_dyn_trial(int64_t n_pairs, const int32_
   const double* sn = s + 10;
   double x[6] = {s[0], s[1], s[2], s[7], s[8], s[9]};
   const int nh = num_hops(g, mode);
-  for (int k = 0; k < nh; k++) rk4_step(x, hop_size(g, mode, k));
+  for (int k = 0; k < nh; k++) rk4_step<true>(x, hop_size(g, mode, k));
   const double r0 = x[0] - sn[0], r1 = x[1] - sn[1], r2 = x[2] - sn[2];
   const double r3 = (x[3] - sn[7]) * vc, r4 = (x[4] - sn[8]) * vc, r5 = (x[5] - sn[9]) * vc;
   const double dt = qdot(qmul(load_q(s), load_q4(crot + f * 4)), load_q(sn));
