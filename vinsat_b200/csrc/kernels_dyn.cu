@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(128) k_dynamics_stm(int64_t n_pairs, const int
 int launch_dynamics_stm(vinsat_ctx* ctx, int64_t n_pairs, const int32_t* order, const double* st,
                         const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred, double* mrec) {
   if (n_pairs == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_DYNAMICS, k_dynamics_stm, ceil_div(n_pairs * 2, 128), 128, 0, n_pairs, order, st, gap, vel_coeff,
+  static const int th = getenv("VINSAT_DYN_THREADS") ? atoi(getenv("VINSAT_DYN_THREADS")) : 32;   // 198 registers: 32-thread CTAs pack 10 warps per SM (128-thread CTAs: 8)
+  VS_LAUNCH(ctx, F_DYNAMICS, k_dynamics_stm, ceil_div(n_pairs * 2, th), th, 0, n_pairs, order, st, gap, vel_coeff,
             mode, drec, x_pred, mrec);
   return VINSAT_OK;
 }
