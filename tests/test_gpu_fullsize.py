@@ -1,0 +1,70 @@
+"""BASELINE.json configs[1] at FULL size (1024 problems x 1000 frames x 10 obs/frame, the bench workload), checked
+through size-independent properties: convergence to the simulated truth, bit-reproducibility, independence of the
+problems of a batch (a sub-batch goes through the PARTITIONED solver path, the full batch through the two-sided
+fused sweep: two different factorisations of the same systems), and the headline residual/Jacobian kernel against
+the oracle on a random sample of the 10.24 M observations."""
+import numpy as np
+import pytest
+
+import ba_oracle as o
+from vinsat_b200 import _lib, synth
+
+pytestmark = pytest.mark.gpu
+
+P, T, K = 1024, 1000, 10
+
+
+@pytest.fixture(scope="module")
+def solved():
+    ctx = _lib.Context(0)
+    prs = synth.make_batch(P, T, K, seed0=0)
+    arrays = _lib.concat_problems(prs)
+    b = _lib.Batch(ctx, arrays)
+    b.eval_resjac()
+    r, J = b.fetch_resjac()
+    b.od_solve(20, 10, 1e-4)
+    st1 = b.get_states().copy()
+    b.upload(arrays)
+    b.od_solve(20, 10, 1e-4)
+    st2 = b.get_states().copy()
+    b.close()
+    yield ctx, prs, arrays, st1, st2, r, J
+    ctx.close()
+
+
+def test_full_size_converges_and_is_reproducible(solved):
+    ctx, prs, arrays, st1, st2, r, J = solved
+    assert np.array_equal(st1, st2)                                  # no floating-point atomics anywhere
+    fo = arrays["frame_off"]
+    err = np.array([np.abs(st1[fo[p]:fo[p + 1], :3] - prs[p]["states_gt"][:, :3]).max() for p in range(P)])
+    assert np.all(np.isfinite(st1))
+    assert np.median(err) < 0.5 and err.max() < 2.0, (np.median(err), err.max())     # km, 1 px noise at 600 km
+    qn = np.linalg.norm(st1[:, 3:7], axis=1)
+    assert np.abs(qn - 1).max() < 1e-12
+
+
+def test_sub_batch_through_partitioned_path_agrees(solved):
+    ctx, prs, arrays, st1, st2, r, J = solved
+    sel = [0, 17, 500, 1023]
+    sub = _lib.concat_problems([prs[p] for p in sel])
+    b = _lib.Batch(ctx, sub)                                         # 4 problems => partitioned (segmented) solver
+    b.od_solve(20, 10, 1e-4)
+    s = b.get_states()
+    b.close()
+    fo = arrays["frame_off"]
+    for j, p in enumerate(sel):
+        a = st1[fo[p]:fo[p + 1]]
+        d = s[j * T:(j + 1) * T]
+        assert np.abs(a[:, :3] - d[:, :3]).max() < 1e-3 and np.abs(a[:, 7:] - d[:, 7:]).max() < 1e-6     # 1 m, 1 mm/s
+
+
+def test_headline_kernel_sample_vs_oracle(solved):
+    ctx, prs, arrays, st1, st2, r, J = solved
+    rng = np.random.default_rng(0)
+    oo = arrays["obs_off"]
+    for p in rng.integers(0, P, 8):
+        pr = prs[p]
+        uv, Jg = o.landmark_project(pr["states0"], pr["xyz"], pr["intr"], pr["ii"])
+        sl = slice(oo[p], oo[p + 1])
+        assert np.array_equal(r[sl], pr["uv"] - uv)                   # residuals bit-exact
+        assert np.abs(J[sl] - Jg[:, :, :6]).max() <= 1e-9 * np.abs(Jg).max()
