@@ -145,9 +145,10 @@ Segmentation make_segments(const vinsat_ctx* ctx, int64_t P, const int64_t* fram
         S = (int64_t)llround((double)Tp * target_chains / (double)std::max<int64_t>(T, 1));
         S = std::min<int64_t>(S, (int64_t)sqrt((double)Tp));
         if (Tp < 64) S = 1;
-        // measured on B200 (T=1000): the plain sweep is latency bound at ~2.1 us per frame whatever P <= ~1200,
-        // the partitioned one costs ~2.6 ns per frame of the whole batch => partition only below ~5 problems per SM
-        if (P >= 5 * (int64_t)ctx->sm_count) S = 1;
+        // measured on B200 (T=1000, two-sided fused sweep vs partitioned sweep + materialised system): 14.7 k solves/s
+        // either way at P = 256, 21.2 k vs 16.3 k at P = 512, 9.3 k vs 11.8 k at P = 128 => partition below ~1.75
+        // problems per SM
+        if (4 * P >= 7 * (int64_t)ctx->sm_count) S = 1;
       }
       S = std::max<int64_t>(1, std::min<int64_t>(S, Tp));
       if (S > 1) s.partitioned = true;
