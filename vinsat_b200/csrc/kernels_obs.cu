@@ -898,7 +898,17 @@ __global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const i
 int launch_obs_trial(vinsat_batch* b) {
   vinsat_ctx* ctx = b->ctx;
   if (b->T == 0) return VINSAT_OK;
-  if (b->M <= 16 * b->T) {
+  static const int grp = getenv("VINSAT_TRIAL_GROUP") ? atoi(getenv("VINSAT_TRIAL_GROUP")) : 0;
+  if (grp == 2 || (grp == 0 && b->M <= 16 * b->T)) {       // sparse frames: 2 lanes per frame (measured best of 1/2/4/8 at K = 10)
+    VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<2>, ceil_div(b->T * 2, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
+              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
+  } else if (grp == 8) {
+    VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<8>, ceil_div(b->T * 8, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
+              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
+  } else if (grp == 1) {
+    VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<1>, ceil_div(b->T, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
+              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
+  } else if (b->M <= 16 * b->T) {
     VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<4>, ceil_div(b->T * 4, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
               b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
   } else {
