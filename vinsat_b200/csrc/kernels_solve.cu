@@ -1,5 +1,7 @@
 // Per-problem kernels (a5 scale, a6 system build, a7 LM step of SURVEY.md section 8): exact lower-median by radix
 // select, block-tridiagonal normal equations, batched block LU solve with fused retraction, accept test.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -91,13 +93,15 @@ __global__ void __launch_bounds__(256) k_select_pick(unsigned long long* __restr
 // resident and runs all six radix-select passes on chip: one pass over HBM instead of six plus 12 launches.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kSelThreads = 1024;
+constexpr int kSelCand = 2048;      // candidate list: keys that share the digits found so far
 
 __global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const int64_t* __restrict__ obs_off,
                                                              const double* __restrict__ r, double* __restrict__ c_obs) {
-  extern __shared__ __align__(16) unsigned long long sel_keys[];
+  extern __shared__ __align__(16) unsigned long long sel_keys[];      // [n] keys, then [kSelCand] candidates
   __shared__ unsigned int hist[kSelBins];
   __shared__ unsigned int wsum[32];
-  __shared__ unsigned long long s_prefix, s_rank;
+  __shared__ unsigned long long s_prefix, s_rank, s_diff;
+  __shared__ unsigned int s_cnt, s_bincount;
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t k0 = obs_off[p], Mp = obs_off[p + 1] - k0;
   const int n = (int)(2 * Mp);
@@ -105,21 +109,26 @@ __global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const in
     if (tid == 0) c_obs[p] = __longlong_as_double(0x7ff8000000000000LL);
     return;
   }
+  unsigned long long* cand = sel_keys + n;
+  // all copies of the problem's residuals are in flight at once (cp.async, no register round trip)
   for (int i = tid; i < n; i += kSelThreads) {
     const int comp = i >= Mp ? 1 : 0;
-    sel_keys[i] = (unsigned long long)__double_as_longlong(fabs(r[(int64_t)comp * M + k0 + (i - comp * Mp)]));
+    __pipeline_memcpy_async(&sel_keys[i], &r[(int64_t)comp * M + k0 + (i - comp * Mp)], 8);
   }
-  // Bits that are identical in every key carry no information: find the highest differing bit with a block-wide
-  // OR of (key ^ key0) and start the 11-bit digits THERE.  (Starting at bit 63 the first digit is the sign + top
-  // exponent bits, which take 3-4 distinct values => the shared-memory atomics serialise 32-way, and a pass is
-  // wasted.)
-  __shared__ unsigned long long s_diff;
+  __pipeline_commit();
   if (tid == 0) s_diff = 0ull;
+  __pipeline_wait_prior(0);
   __syncthreads();
+  // keys = bit patterns of |r|.  Bits that are identical in every key carry no information: find the highest
+  // differing bit with a block-wide OR of (key ^ key0) and start the 11-bit digits THERE.
   {
-    const unsigned long long key0 = sel_keys[0];
+    const unsigned long long key0 = sel_keys[0] & 0x7fffffffffffffffull;
     unsigned long long d = 0ull;
-    for (int i = tid; i < n; i += kSelThreads) d |= sel_keys[i] ^ key0;
+    for (int i = tid; i < n; i += kSelThreads) {
+      const unsigned long long key = sel_keys[i] & 0x7fffffffffffffffull;
+      sel_keys[i] = key;
+      d |= key ^ key0;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d |= __shfl_xor_sync(0xffffffffu, d, o);
     if (lane == 0 && d) atomicOr(&s_diff, d);
@@ -131,22 +140,28 @@ __global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const in
     s_prefix = hi >= 64 ? 0ull : ((sel_keys[0] >> hi) << hi);
     s_rank = (unsigned long long)((n - 1) / 2);
   }
+  // After a pass the keys that matter are those in the selected bin.  If they fit the candidate list they are
+  // compacted into it and the remaining passes scan only them (typically a few dozen keys instead of 2 M_p).
+  const unsigned long long* list = sel_keys;
+  int nlist = n;
+  bool all_match = true;          // every key of `list` shares the prefix found so far
 #pragma unroll 1
   while (hi > 0) {
     const int nb = min(11, hi), shift = hi - nb, hs = hi;
     for (int i = tid; i < kSelBins; i += kSelThreads) hist[i] = 0;
+    if (tid == 0) s_cnt = 0;
     __syncthreads();
     const unsigned long long pre = s_prefix;
     const unsigned int dmask = (1u << nb) - 1u;
-    for (int i = tid; i < n; i += kSelThreads) {
-      const unsigned long long key = sel_keys[i];
-      const bool match = hs >= 64 ? true : ((key >> hs) == (pre >> hs));
+    for (int i = tid; i < nlist; i += kSelThreads) {
+      const unsigned long long key = list[i];
+      const bool match = (all_match || hs >= 64) ? true : ((key >> hs) == (pre >> hs));
       if (match) atomicAdd(&hist[(unsigned int)(key >> shift) & dmask], 1u);
     }
     __syncthreads();
     // each thread owns bins 2*tid, 2*tid+1; block-wide exclusive scan of the pair sums
     const unsigned int h0 = hist[2 * tid], h1 = hist[2 * tid + 1];
-    unsigned int s = h0 + h1, incl = s;
+    unsigned int sum2 = h0 + h1, incl = sum2;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
     if (lane == 31) wsum[warp] = incl;
@@ -158,16 +173,32 @@ __global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const in
       wsum[lane] = wi - w;          // exclusive prefix of the warp sums
     }
     __syncthreads();
-    const unsigned long long before = (unsigned long long)wsum[warp] + (incl - s);
+    const unsigned long long before = (unsigned long long)wsum[warp] + (incl - sum2);
     const unsigned long long rk = s_rank;
     __syncthreads();
-    if (rk >= before && rk < before + s) {
+    if (rk >= before && rk < before + sum2) {
       const int bin = (rk < before + h0) ? 2 * tid : 2 * tid + 1;
       s_prefix = pre | ((unsigned long long)bin << shift);
       s_rank = rk - (bin == 2 * tid ? before : before + h0);
+      s_bincount = (bin == 2 * tid) ? h0 : h1;
     }
     __syncthreads();
     hi = shift;
+    const unsigned int bc = s_bincount;
+    if (hi > 0 && list == sel_keys && bc <= (unsigned int)kSelCand) {
+      // compact the selected bin (order is irrelevant: the k-th smallest of a set does not depend on it)
+      const unsigned long long npre = s_prefix;
+      for (int i = tid; i < nlist; i += kSelThreads) {
+        const unsigned long long key = list[i];
+        if ((key >> shift) == (npre >> shift)) cand[atomicAdd(&s_cnt, 1u)] = key;
+      }
+      __syncthreads();
+      list = cand;
+      nlist = (int)bc;
+      all_match = true;
+    } else {
+      all_match = false;
+    }
   }
   if (tid == 0) c_obs[p] = __longlong_as_double((long long)s_prefix);
 }
@@ -216,9 +247,9 @@ int launch_select_median(vinsat_batch* b) {
   if (b->P == 0) return VINSAT_OK;
   static const bool no_smem = getenv("VINSAT_SELECT_GLOBAL") != nullptr;
   const int64_t keys = 2 * b->max_obs_per_problem;
-  if (!no_smem && keys > 0 && keys <= 26000 && !b->window) {
+  if (!no_smem && keys > 0 && keys <= 24000 && !b->window) {
     vinsat_ctx* ctx = b->ctx;
-    const int smem = (int)(keys * sizeof(unsigned long long));
+    const int smem = (int)((keys + kSelCand) * sizeof(unsigned long long));
     static int attr_smem = 0;
     if (smem > attr_smem) {
       VS_CUDA(ctx, cudaFuncSetAttribute(k_select_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
