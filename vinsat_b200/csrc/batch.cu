@@ -39,6 +39,8 @@ void free_all(vinsat_batch* b) {
                   b->la_xsep, b->la_sums, b->la_edge, b->la_edges_all, b->la_chain};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  b->graphs.clear();
   if (b->h_flags) cudaFreeHost(b->h_flags);
 }
 
@@ -173,6 +175,14 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
     return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_upload: sizes differ from the batch (P,T,M)");
   cudaStream_t s = ctx->stream;
   const int64_t P = b->P, T = b->T, M = b->M;
+  // captured iteration graphs bake in launch shapes derived from the offsets: drop them if the layout changes
+  if (!b->graphs.empty() && (!std::equal(d->frame_off, d->frame_off + P + 1, b->frame_off.begin()) ||
+                             !std::equal(d->obs_off, d->obs_off + P + 1, b->obs_off.begin()))) {
+    VS_CUDA(ctx, cudaStreamSynchronize(s));
+    for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    b->graphs.clear();
+    b->graph_warm.clear();
+  }
   b->frame_off.assign(d->frame_off, d->frame_off + P + 1);
   b->obs_off.assign(d->obs_off, d->obs_off + P + 1);
   b->max_obs_per_problem = 0;
@@ -343,17 +353,29 @@ int vinsat_batch_get_states(vinsat_batch* b, int mem, double* states_out) {
   return VINSAT_OK;
 }
 
-// One BA() call for every problem of the batch; lam_dev_in holds lamda_init per problem on the device.
-static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode, const double* lam_dev_in) {
+// One LM trial: solve, retract, trial residuals, accept test, copy of the "still active" counter to the host.
+static int issue_trial(vinsat_batch* b, int initialize, int mode, double Sigma, double quat_coeff, double vel_coeff) {
+  vinsat_ctx* ctx = b->ctx;
+  VS_TRY(launch_solve_retract(b, initialize));
+  VS_TRY(launch_obs_trial(b));
+  if (!initialize)
+    VS_TRY(launch_dyn_trial(ctx, b->n_pairs, b->dyn_order, b->st_new, b->crot, b->gap, b->active, b->fprob,
+                            quat_coeff, vel_coeff, mode, b->e_dyn, nullptr));
+  VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, sizeof(int32_t), ctx->stream));
+  VS_TRY(launch_accept(b, initialize, Sigma));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->h_flags, b->flags, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  return VINSAT_OK;
+}
+
+// Linearisation + first trial of one BA() call (everything that does not depend on a host decision).
+static int issue_iteration_head(vinsat_batch* b, int iter, int initialize, int mode, const double* lam_dev_in,
+                                bool have_residuals) {
   vinsat_ctx* ctx = b->ctx;
   const double quat_coeff = 100.0, vel_coeff = 100.0;                                  // BA_filtering.py:11-12
   const double alpha = std::min(std::max(1.0 - (2.0 * ((double)iter / 5.0) - 1.0), 1.0), 2.0);   // :22
   const double it1 = (double)iter + 1.0;
   const double Sigma = std::min(10000.0 * it1 * it1, 1000000.0);                       // :26
-  // the last LM trial of the previous call already evaluated uv - project(states) at the returned states
-  // (bit-identical arithmetic), so its residuals are reused instead of projecting every observation again
-  if (b->r_valid) std::swap(b->r, b->r_next);
-  else VS_TRY(launch_obs_residual(b));
+  if (!have_residuals) VS_TRY(launch_obs_residual(b));
   VS_TRY(launch_select_median(b));
   VS_TRY(launch_obs_assemble(b, alpha));
   if (!initialize) {
@@ -364,25 +386,69 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
   // the full records are only materialised on demand (last_hessian / debug_fetch).
   // The plain (unpartitioned) sweep builds its columns on the fly from the per-frame records (fused system
   // build); the partitioned sweep and the diagnostics read the materialised records.
+  if (!initialize && !b->fused_system) VS_TRY(launch_system_build(b, 0, Sigma, vel_coeff));
+  VS_TRY(launch_init_residual(b, initialize, Sigma, 0.0, lam_dev_in));
+  return issue_trial(b, initialize, mode, Sigma, quat_coeff, vel_coeff);
+}
+
+// One BA() call for every problem of the batch; lam_dev_in holds lamda_init per problem on the device.
+static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode, const double* lam_dev_in) {
+  vinsat_ctx* ctx = b->ctx;
+  const double quat_coeff = 100.0, vel_coeff = 100.0;
+  const double it1 = (double)iter + 1.0;
+  const double Sigma = std::min(10000.0 * it1 * it1, 1000000.0);
+  // the last LM trial of the previous call already evaluated uv - project(states) at the returned states
+  // (bit-identical arithmetic), so its residuals are reused instead of projecting every observation again
+  const bool have_residuals = b->r_valid;
+  if (have_residuals) std::swap(b->r, b->r_next);
   static const bool no_fuse = getenv("VINSAT_NO_FUSED_SYSTEM") != nullptr || getenv("VINSAT_ONE_SIDED_SWEEP") != nullptr;
   b->fused_system = !initialize && !b->partitioned && !no_fuse;
-  if (!initialize && !b->fused_system) VS_TRY(launch_system_build(b, 0, Sigma, vel_coeff));
   b->srec_valid = !initialize && !b->fused_system;
   b->last_sigma = Sigma;
   b->cur_sigma = Sigma;
   b->cur_vc = vel_coeff;
-  VS_TRY(launch_init_residual(b, initialize, Sigma, 0.0, lam_dev_in));
+
+  // The head of the iteration (10-12 launches) is replayed as ONE CUDA graph: with several ranks per host the
+  // per-launch host cost dominated the step (8 GPUs: 39 ms of kernels in a 50 ms step).  A key is captured the
+  // second time it is seen, so that every one-time host action (function attributes, scratch growth) has happened.
+  static const bool no_graph = getenv("VINSAT_NO_GRAPH") != nullptr;
+  bool done = false;
+  if (!no_graph && !ctx->timing && !b->window && lam_dev_in == b->lam_next) {
+    if (!b->st_base) { b->st_base = b->st; b->r_base = b->r; }
+    const uint64_t key = (uint64_t)(iter & 0xffff) | ((uint64_t)(initialize ? 1 : 0) << 16) | ((uint64_t)(mode & 0xf) << 17) |
+                         ((uint64_t)(b->st == b->st_base ? 1 : 0) << 21) | ((uint64_t)(b->r == b->r_base ? 1 : 0) << 22) |
+                         ((uint64_t)(have_residuals ? 1 : 0) << 23) | ((uint64_t)(b->fused_system ? 1 : 0) << 24);
+    auto it = b->graphs.find(key);
+    if (it == b->graphs.end() && b->graph_warm.count(key)) {
+      cudaGraph_t g = nullptr;
+      const int64_t l0 = ctx->launches;
+      VS_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = issue_iteration_head(b, iter, initialize, mode, lam_dev_in, have_residuals);
+      const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+      if (rc != VINSAT_OK) { if (g) cudaGraphDestroy(g); return rc; }
+      VS_CUDA(ctx, ce);
+      vinsat_batch::IterGraph ig;
+      ig.n_launches = ctx->launches - l0;
+      ctx->launches = l0;
+      const cudaError_t ie = cudaGraphInstantiate(&ig.exec, g, 0);
+      cudaGraphDestroy(g);
+      VS_CUDA(ctx, ie);
+      it = b->graphs.emplace(key, ig).first;
+    }
+    if (it != b->graphs.end()) {
+      VS_CUDA(ctx, cudaGraphLaunch(it->second.exec, ctx->stream));
+      ctx->launches += it->second.n_launches;
+      done = true;
+    } else {
+      b->graph_warm.insert(key);
+    }
+  }
+  if (!done) VS_TRY(issue_iteration_head(b, iter, initialize, mode, lam_dev_in, have_residuals));
   for (int trial = 0; trial < 16; trial++) {
-    VS_TRY(launch_solve_retract(b, initialize));
-    VS_TRY(launch_obs_trial(b));
-    if (!initialize)
-      VS_TRY(launch_dyn_trial(ctx, b->n_pairs, b->dyn_order, b->st_new, b->crot, b->gap, b->active, b->fprob,
-                              quat_coeff, vel_coeff, mode, b->e_dyn, nullptr));
-    VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, sizeof(int32_t), ctx->stream));
-    VS_TRY(launch_accept(b, initialize, Sigma));
-    VS_CUDA(ctx, cudaMemcpyAsync(b->h_flags, b->flags, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (b->h_flags[0] == 0) break;
+    if (trial == 15) break;
+    VS_TRY(issue_trial(b, initialize, mode, Sigma, quat_coeff, vel_coeff));
   }
   std::swap(b->st, b->st_new);     // every problem's last trial is returned, accepted or not (:60,98)
   b->r_valid = true;

@@ -1,5 +1,7 @@
 // Device-resident batch of OD problems (internal).
 #pragma once
+#include <map>
+#include <set>
 #include "internal.h"
 
 // Per-frame record sizes (doubles).
@@ -55,6 +57,13 @@ struct vinsat_batch {
   double* r = nullptr;         // [2][M] residuals
   double* r_next = nullptr;    // [2][M] residuals at the last trial's states = next iteration's residuals
   bool r_valid = false;
+  // CUDA graphs of one BA iteration up to and including its first LM trial, keyed by everything the captured
+  // launches depend on (iteration index, phase, propagator, which of the ping-pong buffers is current)
+  struct IterGraph { cudaGraphExec_t exec = nullptr; int64_t n_launches = 0; };
+  std::map<uint64_t, IterGraph> graphs;
+  std::set<uint64_t> graph_warm;      // keys that ran eagerly once (function attributes set, scratch grown)
+  const double* st_base = nullptr;    // identity of the ping-pong buffers at creation
+  const double* r_base = nullptr;
   double* wu = nullptr;        // [M] conf * w_raw (un-normalised robust weight)
   double* J = nullptr;         // [12][M] headline kernel output (allocated on first use)
   // ---- device, per problem ----
