@@ -353,6 +353,25 @@ int vinsat_batch_get_states(vinsat_batch* b, int mem, double* states_out) {
   return VINSAT_OK;
 }
 
+// Wait for the "still active" counter of the trial in flight.  The host polls the pinned word the trial's
+// device-to-host copy overwrites (h_flags[0] was set to -1 before the launch) instead of entering
+// cudaStreamSynchronize: with 8 ranks on one host the driver's blocking wait cost ~0.4 ms per trial.
+static int wait_flag(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  static const bool no_spin = getenv("VINSAT_NO_SPIN_WAIT") != nullptr;
+  if (!no_spin) {
+    volatile int32_t* f = b->h_flags;
+    for (int64_t spins = 0; spins < 400000000ll; spins++) {
+      if (f[0] != -1) return VINSAT_OK;
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VINSAT_OK;
+}
+
 // One LM trial: solve, retract, trial residuals, accept test, copy of the "still active" counter to the host.
 static int issue_trial(vinsat_batch* b, int initialize, int mode, double Sigma, double quat_coeff, double vel_coeff) {
   vinsat_ctx* ctx = b->ctx;
@@ -408,12 +427,16 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
   b->cur_sigma = Sigma;
   b->cur_vc = vel_coeff;
 
-  // The head of the iteration (10-12 launches) is replayed as ONE CUDA graph: with several ranks per host the
-  // per-launch host cost dominated the step (8 GPUs: 39 ms of kernels in a 50 ms step).  A key is captured the
-  // second time it is seen, so that every one-time host action (function attributes, scratch growth) has happened.
+  // Small batches are launch bound: the head of the iteration (10-12 launches) is replayed as ONE CUDA graph.  A key
+  // is captured the second time it is seen, so that every one-time host action (function attributes, scratch
+  // growth) has happened.
   static const bool no_graph = getenv("VINSAT_NO_GRAPH") != nullptr;
   bool done = false;
-  if (!no_graph && !ctx->timing && !b->window && lam_dev_in == b->lam_next) {
+  b->h_flags[0] = -1;                 // sentinel: overwritten by the trial's device-to-host copy of the counter
+  // Measured on B200: P = 64 x T = 1000 gains 24 % from the replay (launch bound), P = 1024 LOSES 5 % (20 distinct
+  // graphs of long kernels: the per-graph launch cost exceeds the 10 stream launches it replaces) => small batches only.
+  static const int64_t graph_max_frames = getenv("VINSAT_GRAPH_MAX_FRAMES") ? atoll(getenv("VINSAT_GRAPH_MAX_FRAMES")) : 200000;
+  if (!no_graph && b->T <= graph_max_frames && !ctx->timing && !b->window && lam_dev_in == b->lam_next) {
     if (!b->st_base) { b->st_base = b->st; b->r_base = b->r; }
     const uint64_t key = (uint64_t)(iter & 0xffff) | ((uint64_t)(initialize ? 1 : 0) << 16) | ((uint64_t)(mode & 0xf) << 17) |
                          ((uint64_t)(b->st == b->st_base ? 1 : 0) << 21) | ((uint64_t)(b->r == b->r_base ? 1 : 0) << 22) |
@@ -445,9 +468,10 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
   }
   if (!done) VS_TRY(issue_iteration_head(b, iter, initialize, mode, lam_dev_in, have_residuals));
   for (int trial = 0; trial < 16; trial++) {
-    VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VS_TRY(wait_flag(b));
     if (b->h_flags[0] == 0) break;
     if (trial == 15) break;
+    b->h_flags[0] = -1;
     VS_TRY(issue_trial(b, initialize, mode, Sigma, quat_coeff, vel_coeff));
   }
   std::swap(b->st, b->st_new);     // every problem's last trial is returned, accepted or not (:60,98)
