@@ -169,6 +169,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    cores = _lib.bind_host_thread_to_gpu(local)          # NUMA-local host cores for this rank's launches / polls
     dev = torch.device("cuda", local)
     ctx = _lib.Context(local)
     stream = torch.cuda.Stream(device=dev)
@@ -227,13 +228,31 @@ def run_gpu(args):
 
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local)
     l0 = ctx.launch_count()
     tw0 = time.time()
-    dev_s, wall_s = timed(step_resident, args.steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    torch.cuda.synchronize()
+    own_dev_s = e0.elapsed_time(e1) * 1e-3                 # this rank's own device time, before the closing barrier
+    sync_all()
+    dev_s, wall_s = max_over_ranks(own_dev_s), max_over_ranks(time.perf_counter() - t0)
     tw1 = time.time()
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop(tw0, tw1) if sampler else None
+    clocks = sampler.stop(tw0, tw1)
+    per_rank = [None] * world
+    mine = {"rank": rank, "ms_per_step": round(1e3 * own_dev_s / args.steps, 3), "host_cores": len(cores) if cores else None,
+            "sm_mhz": clocks.get("sm_mhz"),
+            "reasons": clocks.get("reasons"), "power_w_max": clocks.get("power_w_max")}
+    if world > 1:
+        dist.all_gather_object(per_rank, mine)
+    else:
+        per_rank = [mine]
     # per-kernel table: a second pass of the same steps with the library's per-launch CUDA events switched on (that
     # pass launches every kernel individually; the timed pass above replays each iteration's head as a CUDA graph)
     ctx.enable_timing(True); ctx.reset_timing()
@@ -343,7 +362,7 @@ def run_gpu(args):
             "roofline": roofline,
             "cpu_baseline": cb,
             "extra": {
-                "wall_ms_per_step": 1e3 * wall_s / args.steps,
+                "wall_ms_per_step": 1e3 * wall_s / args.steps, "per_rank": per_rank,
                 "ms_per_step_with_per_launch_events": 1e3 * ev_dev_s / args.steps,
                 "resjac_evals_per_s": evals, "resjac_roofline": rj_roof,
                 "kernel_ms_per_step": fam_ms, "kernels": kern, "fp64_peak_tflops_measured": fp64_peak,

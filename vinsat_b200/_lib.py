@@ -282,6 +282,33 @@ class Context:
         return corners, hit
 
 
+def bind_host_thread_to_gpu(device):
+    """Pin the calling process to the CPU cores NVML reports as local to `device` (NUMA node of the GPU's PCIe
+    root).  One process per GPU drives ~200 launches and 20 host round trips per OD solve; on a two-socket host a
+    rank scheduled on the far socket ran 15-20 % slower (bench, 8 x B200).  Returns the core list or None."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        # NVML enumerates all GPUs; map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is a plain list
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device
+        if vis:
+            parts = [v.strip() for v in vis.split(",") if v.strip()]
+            if device < len(parts) and parts[device].isdigit():
+                idx = int(parts[device])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < n_cpu]
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return cores
+    except Exception:
+        pass
+    return None
+
+
 _default_ctx = {}
 
 

@@ -26,6 +26,8 @@ def run_od_monte_carlo(n_problems, frames=1000, obs_per_frame=10, seed0=0, sigma
     from .. import _lib, config, synth
     lo = (n_problems * rank) // world_size
     hi = (n_problems * (rank + 1)) // world_size
+    if world_size > 1:
+        _lib.bind_host_thread_to_gpu(config.device if device is None else device)
     ctx = _lib.default_context(config.device if device is None else device)
     prs = synth.make_batch(hi - lo, frames, obs_per_frame, seed0=seed0 + lo, sigma_px=sigma_px)
     arrays = _lib.concat_problems(prs)
