@@ -11,12 +11,15 @@
 // small block-tridiagonal REDUCED system (one 9x9 row per segment) which the same elimination solves (plain
 // mode, explicit lower blocks).  A last pass back-substitutes the interiors.
 //
-// Mapping: ONE WARP PER CHAIN.  The augmented block [S | U | b | Z] (9 x 28) is held one COLUMN per lane
-// (lanes 0-8 S, 9-17 U, 18 b, 19-27 Z; 9 registers each), so control flow is uniform inside a warp and the
-// code stays small enough for the instruction cache (a first version with 4 chains per warp compiled to
-// 84 KB of SASS and was instruction-fetch bound).  Gauss-Jordan without pivoting (the symmetric part of every
-// pivot block is positive definite); the pivot column is broadcast through shared memory.
-// Parallelism comes from the number of chains (P x segments), ~35 resident warps per SM at P = 1024.
+// The Monte-Carlo path (many problems) needs no segments: every problem is swept from BOTH ends towards its middle
+// frame (two chains per problem, same flops as a one-sided sweep, half the sequential length), the middle 9x9
+// system couples the halves, and the back-substitution runs outward from it.
+//
+// Mapping: THREE CHAINS PER WARP, 10 lanes per chain; a lane holds one column of EACH of [S | b], [U] and (segment
+// mode) [Z], 9 registers per column, so control flow is uniform inside a warp.  Block Gauss-Jordan with 3x3 pivots
+// and no pivoting (the symmetric part of every pivot block is positive definite); the pivot columns
+// are broadcast through shared memory.  On the Monte-Carlo path the columns are assembled on the fly from the
+// per-frame assembly records (fused system build).
 #include <cuda_pipeline.h>
 
 #include "common.cuh"
@@ -272,164 +275,8 @@ __device__ __forceinline__ void gj_block3(double (&a_)[9], const int c, double (
   }
 }
 
-constexpr int kFwdWarps = 2;    // 2 chains per CTA: 2P chains spread evenly over the 148 SMs (4 per CTA left 27 % of the SMs with half the work)
-
 // ---------------------------------------------------------------------------------------------------------
-// forward elimination of one chain per warp.  SPIKE=true: segment mode (Z columns + left-part record).
-// ---------------------------------------------------------------------------------------------------------
-template <bool SPIKE>
-__global__ void __launch_bounds__(kFwdWarps * 32, 16 / kFwdWarps) k_chain_forward(ChainArgs A) {
-  __shared__ __align__(16) double s_col[kFwdWarps][2][3][kMS];
-  __shared__ __align__(16) double s_M[kFwdWarps][9 * kMS];
-  __shared__ __align__(16) double s_W[kFwdWarps][10 * 9];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ch = blockIdx.x * kFwdWarps + warp;
-  if (ch >= A.n_chains) return;
-  const int prob = A.ch_prob[ch];
-  if (A.active && !A.active[prob]) return;
-  const int a = A.ch_a[ch], e = A.ch_b[ch];
-  const int dir = (!SPIKE && A.ch_dir) ? A.ch_dir[ch] : 1;
-  const int left = SPIKE ? A.ch_left[ch] : -1;
-  double lam32 = 0.0;
-  if (A.lam) {
-    lam32 = (double)(float)A.lam[prob];           // torch.eye(n)*lamda is float32
-    if (A.lam32_last && lane == 0) A.lam32_last[prob] = lam32;
-  }
-  const int c = lane;
-  // column roles
-  const bool isS = c < 9, isU = c >= 9 && c < 18, isB = c == 18, isZ = SPIKE && c >= 19 && c < 28;
-  const int cc = isS ? c : (isU ? c - 9 : (isZ ? c - 19 : 0));       // column index inside its block
-  // offset of element (r, c) inside a system record.  A bottom chain (dir -1) couples element i to i-1 through
-  // A(i, i-1) = U_{i-1}^T: its U lanes read the record of element i-1, transposed (contiguous rows).
-  const bool rev = dir < 0;
-  const int base = isS ? c : (isU ? (rev ? 81 + (c - 9) * 9 : 81 + (c - 9)) : 162);
-  const int rstride = (isB || (isU && rev)) ? 1 : 9;
-  const int joff = (isU && rev) ? -1 : 0;
-  const bool loads = isS || isU || isB;
-  double (*colk3)[3][kMS] = s_col[warp];
-  double* M = s_M[warp];
-  double* Ws = s_W[warp];
-  double* rr = SPIKE ? A.redrec + (int64_t)ch * VS_RREC : nullptr;
-  const int len = (e - a) * dir;
-  double* midrec = (!SPIKE && A.mid) ? A.mid + (int64_t)ch * VS_MIDREC : nullptr;
-
-  if (midrec && len <= 0) {
-    for (int idx = lane; idx < 90; idx += 32) midrec[idx] = 0.0;
-    return;
-  }
-  if (SPIKE && len == 0) {
-    // no interior: the separator couples directly to the left separator.  Ll = Lo_left, Dl = bl = 0.
-    for (int idx = lane; idx < 171; idx += 32) {
-      double v = 0.0;
-      if (idx >= 81 && idx < 162 && left >= 0) {
-        const int r = (idx - 81) / 9, k = (idx - 81) % 9;
-        v = A.lrec ? A.lrec[(int64_t)left * 81 + r * 9 + k] : A.rec[(int64_t)left * VS_SREC + 81 + k * 9 + r];
-      }
-      rr[idx] = v;
-    }
-    return;
-  }
-  if (len <= 0) return;
-
-  double a_[9], nxt[9], corr[9];
-#pragma unroll
-  for (int r = 0; r < 9; r++) { corr[r] = 0.0; nxt[r] = 0.0; a_[r] = 0.0; }
-  if (loads) {
-    const double* rec = A.rec + (int64_t)(a + joff) * VS_SREC;
-#pragma unroll
-    for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
-  }
-  if (isZ && left >= 0) {
-    // Z~_a = Lo_left: column cc.  explicit: Lo[r][cc]; base: Lo[r][cc] = U_left[cc][r].  Stored NEGATED in corr
-    // because the assembly below uses a = nxt - corr.
-    if (A.lrec) {
-#pragma unroll
-      for (int r = 0; r < 9; r++) corr[r] = -A.lrec[(int64_t)left * 81 + r * 9 + cc];
-    } else {
-#pragma unroll
-      for (int r = 0; r < 9; r++) corr[r] = -A.rec[(int64_t)left * VS_SREC + 81 + cc * 9 + r];
-    }
-  }
-
-  for (int i = a; i != e; i += dir) {
-    const bool more = (i + dir != e);
-    // assemble the augmented column of element i:  S: D + lam I - Lo W;  U: fresh;  b: b - Lo y;  Z: -Lo Z
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-      double v = nxt[r];
-      if (isS) v += (r == c ? lam32 : 0.0) - corr[r];
-      else if (isB || isZ) v -= corr[r];
-      a_[r] = v;
-    }
-    if (more && loads) {
-      const double* rec = A.rec + (int64_t)(i + dir + joff) * VS_SREC;
-#pragma unroll
-      for (int r = 0; r < 9; r++) nxt[r] = rec[base + r * rstride];
-    }
-    // lower block Lo_i staged as M[k*kMS + r] = Lo_i[r][k]
-    if (A.lrec) {
-      const double* L = A.lrec + (int64_t)i * 81;
-      for (int idx = lane; idx < 81; idx += 32) { const int r = idx / 9, k = idx % 9; M[k * kMS + r] = L[idx]; }
-    } else if (isU) {
-#pragma unroll
-      for (int r = 0; r < 9; r++) M[r * kMS + cc] = a_[r];       // M[k][r'] = U[k][r'] = Lo[r'][k]
-    }
-    gj_block3(a_, c, colk3);
-    // publish W (lanes 9..17) and y (lane 18) for the S / b lanes; store W, y, Z
-    if (isU || isB) {
-#pragma unroll
-      for (int r = 0; r < 9; r++) Ws[(c - 9) * 9 + r] = a_[r];
-    }
-    {
-      double* w = A.wrec + (int64_t)i * VS_WREC;
-      if (isU || isB) {
-#pragma unroll
-        for (int r = 0; r < 9; r++) w[(c - 9) * 9 + r] = a_[r];
-      } else if (isZ) {
-#pragma unroll
-        for (int r = 0; r < 9; r++) w[90 + cc * 9 + r] = a_[r];
-      }
-    }
-    __syncwarp();
-    // corr = Lo_i x (W_c | y | Z_c): for element i+1, and (segment mode) for the separator's row after the loop
-    if (more || SPIKE || midrec) {
-      if (isS || isB || isZ) {
-        double v[9];
-        if (isZ) {
-#pragma unroll
-          for (int k = 0; k < 9; k++) v[k] = a_[k];
-        } else {
-          const double* wc = Ws + (isS ? c : 9) * 9;
-#pragma unroll
-          for (int k = 0; k < 9; k++) v[k] = wc[k];
-        }
-        matvec9(M, v, corr);
-      }
-    }
-    __syncwarp();
-  }
-
-  if (midrec) {
-    // contribution of this half to the middle element's row: Lo W (9x9) and Lo y
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-      if (isS) midrec[r * 9 + c] = corr[r];
-      else if (isB) midrec[81 + r] = corr[r];
-    }
-  }
-  if (SPIKE) {
-    // left part of the separator's row: Dl = -Lo W, bl = -Lo y, Ll = -Lo Z (all from the last interior element)
-#pragma unroll
-    for (int r = 0; r < 9; r++) {
-      if (isS) rr[r * 9 + c] = -corr[r];
-      else if (isZ) rr[81 + r * 9 + cc] = -corr[r];
-      else if (isB) rr[162 + r] = -corr[r];
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Forward elimination, THREE CHAINS PER WARP (default).  The one-column-per-lane kernel above is bound by the
+// Forward elimination, THREE CHAINS PER WARP.  A one-column-per-lane version (one warp per chain) was bound by the
 // L1/shared-memory data pipe (ncu: 238 shared wavefronts per frame for the pivot / Lo broadcasts, 75-95 % busy),
 // not by latency, so more resident chains do not help it.  Here a group of 10 lanes owns a chain and every lane
 // holds one column of EACH of [S | b], [U | -] (and [Z | -] in segment mode): a broadcast shared-memory read
@@ -671,15 +518,10 @@ __global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
 
 template <bool SPIKE>
 static int launch_forward(vinsat_ctx* ctx, const ChainArgs& A) {
-  static const bool v1 = getenv("VINSAT_FWD_V1") != nullptr;
-  if (v1 && !A.fused) {
-    VS_LAUNCH(ctx, F_SOLVE, k_chain_forward<SPIKE>, ceil_div(A.n_chains, kFwdWarps), kFwdWarps * 32, 0, A);
+  if (A.fused) {
+    VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<false, true>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
   } else {
-    if (A.fused) {
-      VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<false, true>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
-    } else {
-      VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<SPIKE, false>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
-    }
+    VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<SPIKE, false>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
   }
   return VINSAT_OK;
 }

@@ -254,65 +254,6 @@ __device__ __forceinline__ double robust_component(double r, double c, const Wei
   return pow(base, wp.ex) / c2;
 }
 
-template <int kGroup, int kMinBlocks>
-__global__ void __launch_bounds__(128, kMinBlocks) k_obs_assemble(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
-                                                      const int32_t* __restrict__ fprob,
-                                                      const double* __restrict__ X, const double* __restrict__ uv,
-                                                      const double* __restrict__ conf, const double* __restrict__ st,
-                                                      const double* __restrict__ intr,
-                                                      const double* __restrict__ c_obs, WeightParams wp,
-                                                      double* __restrict__ wu_out, double* __restrict__ grec,
-                                                      unsigned long long* __restrict__ wmax) {
-  const int gl = threadIdx.x & (kGroup - 1);
-  const int64_t f = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kGroup;
-  const bool valid = f < T;     // whole groups are valid or not; keep all lanes for the shuffles
-  double acc[VS_GREC];
-#pragma unroll
-  for (int i = 0; i < VS_GREC; i++) acc[i] = 0.0;
-  double wloc = 0.0;
-  int p = 0;
-  if (valid) {
-    const int k0 = obs_start[f], k1 = obs_start[f + 1];
-    if (k1 > k0) {
-      p = fprob[f];
-      const double c = c_obs[p];
-      const double* s = st + f * 10;
-      const double4 ci = *reinterpret_cast<const double4*>(intr + f * 4);
-      const double px = s[0], py = s[1], pz = s[2];
-      const Quat q = {s[3], s[4], s[5], s[6]};
-      for (int k = k0 + gl; k < k1; k += kGroup) {
-        ProjOut o = project_exact(px, py, pz, q, X[k], X[M + k], X[2 * M + k], ci.x, ci.y, ci.z, ci.w);
-        double ju[6], jv[6];
-        project_jacobian(o, ci.x, ci.y, ju, jv);
-        const double ru = xsub(uv[k], o.u), rv = xsub(uv[M + k], o.v);
-        const double wraw = 0.5 * (robust_component(ru, c, wp) + robust_component(rv, c, wp));
-        const double w = wraw * conf[k];
-        wu_out[k] = w;
-        wloc = fmax(wloc, wraw);
-        int idx = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++) {
-          const double wa_u = w * ju[a], wa_v = w * jv[a];
-#pragma unroll
-          for (int bcol = a; bcol < 6; bcol++) acc[idx++] += wa_u * ju[bcol] + wa_v * jv[bcol];
-          acc[21 + a] += wa_u * ru + wa_v * rv;
-        }
-        acc[27] += fabs(ru) + fabs(rv);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < VS_GREC; i++) acc[i] = group_sum<kGroup>(acc[i]);
-  wloc = group_max<kGroup>(wloc);
-  if (valid) {
-    double* g = grec + f * VS_GREC;
-#pragma unroll
-    for (int i = 0; i < VS_GREC; i++)
-      if ((i & (kGroup - 1)) == gl) g[i] = acc[i];
-    if (gl == 0 && wloc > 0.0) atomicMax(&wmax[p], (unsigned long long)__double_as_longlong(wloc));
-  }
-}
-
 // Same weight with the scale-dependent divisions hoisted out of the per-observation code (1/c, 1/|alpha-2|,
 // 1/c^2 computed once per frame; rsqrt for alpha == 1): a few ulp from robust_component, well inside 1e-12.
 struct FrameWeight { double inv_c, inv_am2, inv_c2; };
@@ -332,136 +273,13 @@ __device__ __forceinline__ double robust_component_fast(double r, const FrameWei
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Camera-frame accumulation (default path).  With J = [-Pi R^T | 2 Pi H], H = hat(p_c), N = w Pi^T Pi (3x3, 5
-// distinct non-zeros) and m = w Pi^T r, the per-frame sums are
+// Camera-frame accumulation.  With J = [-Pi R^T | 2 Pi H], H = hat(p_c), N = w Pi^T Pi (3x3, 5 distinct non-zeros)
+// and m = w Pi^T r, the per-frame sums are
 //     J^T W J = [ R (sum N) R^T      -2 R (sum N H) ]        J^T W r = [ -R (sum m)     ]
 //               [      .             4 sum H^T N H  ]                  [ 2 sum H^T m   ]
 // so each observation only adds 26 camera-frame numbers (no per-observation rotation of the Jacobian) and the
-// rotation into the world frame happens once per frame.  ~150 instructions per observation instead of ~270.
+// rotation into the world frame happens once per frame.
 // ---------------------------------------------------------------------------------------------------------
-template <int kGroup, int kMinBlocks>
-__global__ void __launch_bounds__(128, kMinBlocks) k_obs_assemble_cam(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
-                                                           const int32_t* __restrict__ fprob,
-                                                           const double* __restrict__ X, const double* __restrict__ uv,
-                                                           const double* __restrict__ conf,
-                                                           const double* __restrict__ st,
-                                                           const double* __restrict__ intr,
-                                                           const double* __restrict__ c_obs, WeightParams wp,
-                                                           double* __restrict__ wu_out, double* __restrict__ grec,
-                                                           unsigned long long* __restrict__ wmax) {
-  const int gl = threadIdx.x & (kGroup - 1);
-  const int64_t f = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kGroup;
-  const bool valid = f < T;
-  // sN: n00 n02 n11 n12 n22 | sNH: 9 | sHNH: 6 (upper) | sm: 3 | sHm: 3 | sabs
-  double sN[5] = {0, 0, 0, 0, 0}, sNH[9], sHNH[6] = {0, 0, 0, 0, 0, 0}, sm[3] = {0, 0, 0}, sHm[3] = {0, 0, 0}, sabs = 0.0;
-#pragma unroll
-  for (int i = 0; i < 9; i++) sNH[i] = 0.0;
-  double wloc = 0.0;
-  int p = 0;
-  double Rt[9];     // R^T row-major: p_c = Rt (X - p)
-#pragma unroll
-  for (int i = 0; i < 9; i++) Rt[i] = 0.0;
-  if (valid) {
-    const int k0 = obs_start[f], k1 = obs_start[f + 1];
-    if (k1 > k0) {
-      p = fprob[f];
-      const double c = c_obs[p];
-      const double* s = st + f * 10;
-      const double4 ci = *reinterpret_cast<const double4*>(intr + f * 4);
-      const double px = s[0], py = s[1], pz = s[2];
-      {
-        const double qn = 1.0 / sqrt(s[3] * s[3] + s[4] * s[4] + s[5] * s[5] + s[6] * s[6]);
-        const double x = s[3] * qn, y = s[4] * qn, z = s[5] * qn, w = s[6] * qn;
-        Rt[0] = 1 - 2 * (y * y + z * z); Rt[1] = 2 * (x * y + z * w);     Rt[2] = 2 * (x * z - y * w);
-        Rt[3] = 2 * (x * y - z * w);     Rt[4] = 1 - 2 * (x * x + z * z); Rt[5] = 2 * (y * z + x * w);
-        Rt[6] = 2 * (x * z + y * w);     Rt[7] = 2 * (y * z - x * w);     Rt[8] = 1 - 2 * (x * x + y * y);
-      }
-      for (int k = k0 + gl; k < k1; k += kGroup) {
-        const double dx = X[k] - px, dy = X[M + k] - py, dz = X[2 * M + k] - pz;
-        const double Xc = Rt[0] * dx + Rt[1] * dy + Rt[2] * dz;
-        const double Yc = Rt[3] * dx + Rt[4] * dy + Rt[5] * dz;
-        const double Zc = Rt[6] * dx + Rt[7] * dy + Rt[8] * dz;
-        const double live = (Zc >= 0.1) ? 1.0 : 0.0;
-        const double d = 1.0 / fmax(Zc, 0.1);
-        const double a = ci.x * d, bb = ci.y * d;
-        const double ru = uv[k] - (a * Xc + ci.z), rv = uv[M + k] - (bb * Yc + ci.w);
-        const double cc = -a * Xc * d * live, ee = -bb * Yc * d * live;
-        const double wraw = 0.5 * (robust_component(ru, c, wp) + robust_component(rv, c, wp));
-        const double w = wraw * conf[k];
-        wu_out[k] = w;
-        wloc = fmax(wloc, wraw);
-        sabs += fabs(ru) + fabs(rv);
-        // N = w Pi^T Pi
-        const double wa = w * a, wb = w * bb;
-        const double n00 = wa * a, n02 = wa * cc, n11 = wb * bb, n12 = wb * ee, n22 = w * (cc * cc + ee * ee);
-        sN[0] += n00; sN[1] += n02; sN[2] += n11; sN[3] += n12; sN[4] += n22;
-        // N H, H = hat(p_c)
-        const double h00 = -n02 * Yc, h01 = n02 * Xc - n00 * Zc, h02 = n00 * Yc;
-        const double h10 = n11 * Zc - n12 * Yc, h11 = n12 * Xc, h12 = -n11 * Xc;
-        const double h20 = n12 * Zc - n22 * Yc, h21 = n22 * Xc - n02 * Zc, h22 = n02 * Yc - n12 * Xc;
-        sNH[0] += h00; sNH[1] += h01; sNH[2] += h02; sNH[3] += h10; sNH[4] += h11; sNH[5] += h12;
-        sNH[6] += h20; sNH[7] += h21; sNH[8] += h22;
-        // H^T (N H) = -H (N H), upper triangle
-        sHNH[0] += Zc * h10 - Yc * h20;           // (0,0)
-        sHNH[1] += Zc * h11 - Yc * h21;           // (0,1)
-        sHNH[2] += Zc * h12 - Yc * h22;           // (0,2)
-        sHNH[3] += Xc * h21 - Zc * h01;           // (1,1)
-        sHNH[4] += Xc * h22 - Zc * h02;           // (1,2)
-        sHNH[5] += Yc * h02 - Xc * h12;           // (2,2)
-        // m = w Pi^T r, H^T m = -H m
-        const double m0 = wa * ru, m1 = wb * rv, m2 = w * (cc * ru + ee * rv);
-        sm[0] += m0; sm[1] += m1; sm[2] += m2;
-        sHm[0] += Zc * m1 - Yc * m2; sHm[1] += Xc * m2 - Zc * m0; sHm[2] += Yc * m0 - Xc * m1;
-      }
-    }
-  }
-  if (kGroup > 1) {
-#pragma unroll
-    for (int i = 0; i < 5; i++) sN[i] = group_sum<kGroup>(sN[i]);
-#pragma unroll
-    for (int i = 0; i < 9; i++) sNH[i] = group_sum<kGroup>(sNH[i]);
-#pragma unroll
-    for (int i = 0; i < 6; i++) sHNH[i] = group_sum<kGroup>(sHNH[i]);
-#pragma unroll
-    for (int i = 0; i < 3; i++) { sm[i] = group_sum<kGroup>(sm[i]); sHm[i] = group_sum<kGroup>(sHm[i]); }
-    sabs = group_sum<kGroup>(sabs);
-    wloc = group_max<kGroup>(wloc);
-  }
-  if (valid && gl == 0) {
-    // rotate into the world frame: A = Rt^T N Rt, B = -2 Rt^T (N H), C = 4 H^T N H, g = [-Rt^T m ; 2 H^T m]
-    const double N[9] = {sN[0], 0.0, sN[1], 0.0, sN[2], sN[3], sN[1], sN[3], sN[4]};
-    double NR[9];      // N Rt
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-      for (int j = 0; j < 3; j++) NR[i * 3 + j] = N[i * 3] * Rt[j] + N[i * 3 + 1] * Rt[3 + j] + N[i * 3 + 2] * Rt[6 + j];
-    double out[VS_GREC];
-    // upper triangle of the 6x6 block in (a, b >= a) order: rows 0..2 need A (cols a..2) and B (cols 3..5)
-    int idx = 0;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-#pragma unroll
-      for (int bcol = a; bcol < 3; bcol++)
-        out[idx++] = Rt[a] * NR[bcol] + Rt[3 + a] * NR[3 + bcol] + Rt[6 + a] * NR[6 + bcol];
-#pragma unroll
-      for (int bcol = 0; bcol < 3; bcol++)
-        out[idx++] = -2.0 * (Rt[a] * sNH[bcol] + Rt[3 + a] * sNH[3 + bcol] + Rt[6 + a] * sNH[6 + bcol]);
-    }
-    out[idx++] = 4.0 * sHNH[0]; out[idx++] = 4.0 * sHNH[1]; out[idx++] = 4.0 * sHNH[2];
-    out[idx++] = 4.0 * sHNH[3]; out[idx++] = 4.0 * sHNH[4];
-    out[idx++] = 4.0 * sHNH[5];
-#pragma unroll
-    for (int a = 0; a < 3; a++) out[21 + a] = -(Rt[a] * sm[0] + Rt[3 + a] * sm[1] + Rt[6 + a] * sm[2]);
-#pragma unroll
-    for (int a = 0; a < 3; a++) out[24 + a] = 2.0 * sHm[a];
-    out[27] = sabs;
-    double* g = grec + f * VS_GREC;
-#pragma unroll
-    for (int i = 0; i < VS_GREC; i += 2) *reinterpret_cast<double2*>(g + i) = make_double2(out[i], out[i + 1]);
-    if (wloc > 0.0) atomicMax(&wmax[p], (unsigned long long)__double_as_longlong(wloc));
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Same camera-frame accumulation, observations STAGED THROUGH SHARED MEMORY: a CTA owns 128 consecutive frames
 // (one thread each); their observations form one contiguous range of the SoA arrays, which is copied in chunks
@@ -798,66 +616,26 @@ int launch_obs_assemble(vinsat_batch* b, double alpha) {
   wp.ex_is_mhalf = (wp.ex == -0.5) ? 1 : 0;
   VS_CUDA(ctx, cudaMemsetAsync(b->wmax, 0, b->P * sizeof(unsigned long long), ctx->stream));
   if (b->T == 0) return VINSAT_OK;
-  // 4 lanes per frame for sparse frames (<= 16 observations on average), 8 otherwise
   static int variant = getenv("VINSAT_ASM_VARIANT") ? atoi(getenv("VINSAT_ASM_VARIANT")) : 0;
-#define ASM_LAUNCH(G, MB)                                                                                          \
-  VS_LAUNCH(ctx, F_OBS_ASSEMBLE, (k_obs_assemble<G, MB>), ceil_div(b->T * G, 128), 128, 0, b->T, b->M, b->obs_start, \
-            b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax)
-  const bool sparse = b->M <= 16 * b->T;
-#define CAM_LAUNCH2(G, MB)                                                                                          \
-  VS_LAUNCH(ctx, F_OBS_ASSEMBLE, (k_obs_assemble_cam<G, MB>), ceil_div(b->T * G, 128), 128, 0, b->T, b->M, b->obs_start, \
-            b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax)
-#define CAM_LAUNCH(G) CAM_LAUNCH2(G, 3)
-#define STAGED_LAUNCH(TH, CH, UN, MB)                                                                                          \
-  do {                                                                                                                 \
-    static bool attr_set = false;                                                                                      \
-    const int smem = 6 * CH * (int)sizeof(double);                                                                     \
-    if (!attr_set) {                                                                                                   \
-      VS_CUDA(ctx, cudaFuncSetAttribute(k_obs_assemble_staged<TH, CH, UN, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      attr_set = true;                                                                                                 \
-    }                                                                                                                  \
-    VS_LAUNCH(ctx, F_OBS_ASSEMBLE, (k_obs_assemble_staged<TH, CH, UN, MB>), ceil_div(b->T, TH), TH, smem, b->T, b->M,          \
-              b->obs_start, b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);    \
-    return VINSAT_OK;                                                                                                  \
-  } while (0)
-  if (variant == 30) STAGED_LAUNCH(128, 1408, 1, 3);     // 67.6 KB, 3 CTAs per SM
-  if (variant == 31) STAGED_LAUNCH(64, 704, 1, 6);       // 33.8 KB, 6 CTAs per SM
-  if (variant == 0 || variant == 50) {
+  if (variant == 32) {            // thread-per-frame walk (kept for comparison)
     static bool attr_set = false;
-    const int smem = (k2pSlots * k2pChunk + 32 * k2pFrameRec) * (int)sizeof(double) + k2pChunk * (int)sizeof(int32_t);
+    const int smem = 6 * 352 * (int)sizeof(double);
     if (!attr_set) {
-      VS_CUDA(ctx, cudaFuncSetAttribute(k_obs_assemble_2pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      VS_CUDA(ctx, cudaFuncSetAttribute(k_obs_assemble_staged<32, 352, 1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_set = true;
     }
-    VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_2pass, ceil_div(b->T, 32), 32, smem, b->T, b->M, b->obs_start, b->oframe,
-              b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
+    VS_LAUNCH(ctx, F_OBS_ASSEMBLE, (k_obs_assemble_staged<32, 352, 1, 12>), ceil_div(b->T, 32), 32, smem, b->T, b->M,
+              b->obs_start, b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
     return VINSAT_OK;
   }
-  if (variant == 32) STAGED_LAUNCH(32, 352, 1, 12);      // default: one warp per CTA, 16.9 KB, 12 CTAs per SM
-  if (variant == 33) STAGED_LAUNCH(32, 352, 2, 12);
-  if (variant == 34) STAGED_LAUNCH(32, 352, 2, 8);
-  if (variant == 35) STAGED_LAUNCH(32, 352, 1, 16);
-  if (variant == 36) STAGED_LAUNCH(32, 352, 2, 16);
-#undef STAGED_LAUNCH
-  if (variant == 9) { if (sparse) CAM_LAUNCH2(1, 4); else CAM_LAUNCH(8); return VINSAT_OK; }
-  if (variant == 10) { CAM_LAUNCH(1); return VINSAT_OK; }
-  if (variant == 11) { CAM_LAUNCH(2); return VINSAT_OK; }
-  if (variant == 12) { CAM_LAUNCH(4); return VINSAT_OK; }
-  if (variant == 13) { CAM_LAUNCH(8); return VINSAT_OK; }
-  if (variant == 20) { CAM_LAUNCH2(1, 4); return VINSAT_OK; }
-  if (variant == 21) { CAM_LAUNCH2(2, 4); return VINSAT_OK; }
-  if (variant == 22) { CAM_LAUNCH2(1, 5); return VINSAT_OK; }
-  if (variant == 23) { CAM_LAUNCH2(2, 5); return VINSAT_OK; }
-  if (variant == 24) { CAM_LAUNCH2(1, 6); return VINSAT_OK; }
-#undef CAM_LAUNCH2
-#undef CAM_LAUNCH
-  if (variant == 1) { if (sparse) ASM_LAUNCH(4, 4); else ASM_LAUNCH(8, 4); }
-  else if (variant == 2) { ASM_LAUNCH(8, 3); }
-  else if (variant == 3) { ASM_LAUNCH(8, 4); }
-  else if (variant == 4) { ASM_LAUNCH(2, 3); }
-  else if (variant == 5) { ASM_LAUNCH(2, 4); }
-  else { if (sparse) ASM_LAUNCH(2, 3); else ASM_LAUNCH(8, 3); }
-#undef ASM_LAUNCH
+  static bool attr_set = false;
+  const int smem = (k2pSlots * k2pChunk + 32 * k2pFrameRec) * (int)sizeof(double) + k2pChunk * (int)sizeof(int32_t);
+  if (!attr_set) {
+    VS_CUDA(ctx, cudaFuncSetAttribute(k_obs_assemble_2pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_2pass, ceil_div(b->T, 32), 32, smem, b->T, b->M, b->obs_start, b->oframe,
+            b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
   return VINSAT_OK;
 }
 
@@ -898,18 +676,8 @@ __global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const i
 int launch_obs_trial(vinsat_batch* b) {
   vinsat_ctx* ctx = b->ctx;
   if (b->T == 0) return VINSAT_OK;
-  static const int grp = getenv("VINSAT_TRIAL_GROUP") ? atoi(getenv("VINSAT_TRIAL_GROUP")) : 0;
-  if (grp == 2 || (grp == 0 && b->M <= 16 * b->T)) {       // sparse frames: 2 lanes per frame (measured best of 1/2/4/8 at K = 10)
+  if (b->M <= 16 * b->T) {       // sparse frames: 2 lanes per frame (measured best of 1/2/4/8 at K = 10)
     VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<2>, ceil_div(b->T * 2, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
-              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
-  } else if (grp == 8) {
-    VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<8>, ceil_div(b->T * 8, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
-              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
-  } else if (grp == 1) {
-    VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<1>, ceil_div(b->T, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
-              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
-  } else if (b->M <= 16 * b->T) {
-    VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<4>, ceil_div(b->T * 4, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
               b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
   } else {
     VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<8>, ceil_div(b->T * 8, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,

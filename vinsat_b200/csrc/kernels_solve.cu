@@ -276,85 +276,10 @@ __device__ __forceinline__ int sym_index(int a, int b) {   // upper triangle of 
   return a * 6 - (a * (a - 1)) / 2 + (b - a);
 }
 
-__global__ void __launch_bounds__(256) k_system(int64_t T, const int32_t* __restrict__ gap,
-                                                const int32_t* __restrict__ fprob,
-                                                const unsigned long long* __restrict__ wmax,
-                                                const double* __restrict__ grec, const double* __restrict__ drec,
-                                                int initialize, double Sigma, double vc,
-                                                double* __restrict__ srec) {
-  __shared__ double sm[8][VS_GREC + VS_DREC + 6];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t f = blockIdx.x * 8ll + warp;
-  if (f >= T) return;
-  double* G = sm[warp];
-  double* Dr = G + VS_GREC;
-  double* rp = Dr + VS_DREC;
-  const bool has_next = gap[f] > 0;
-  const bool has_prev = f > 0 && gap[f - 1] > 0;
-  if (lane < VS_GREC) G[lane] = grec[f * VS_GREC + lane];
-  if (!initialize) {
-    Dr[lane] = drec[f * VS_DREC + lane];
-    Dr[lane + 32] = drec[f * VS_DREC + lane + 32];
-    if (lane < 6) rp[lane] = has_prev ? drec[(f - 1) * VS_DREC + 36 + lane] : 0.0;
-  }
-  __syncwarp();
-  const unsigned long long wb = wmax[fprob[f]];
-  const double invw = wb ? 1.0 / __longlong_as_double((long long)wb) : 0.0;
-  const double dv[6] = {1.0, 1.0, 1.0, vc, vc, vc};
-  double* out = srec + f * VS_SREC;
-  for (int e = lane; e < 171; e += 32) {
-    double val = 0.0;
-    if (e < 81) {
-      const int a = e / 9, c = e % 9;
-      if (a < 6 && c < 6) val = invw * G[a <= c ? sym_index(a, c) : sym_index(c, a)];
-      if (!initialize) {
-        const int pa = pv_index(a), pc = pv_index(c);
-        if (pa >= 0 && pc >= 0) {
-          if (has_next) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) s += Dr[k * 6 + pa] * (dv[k] * dv[k]) * Dr[k * 6 + pc];
-            val += Sigma * s;
-          }
-          if (has_prev && pa == pc) val += Sigma * dv[pa] * dv[pa];
-        } else if (pa < 0 && pc < 0) {
-          val += Sigma * Dr[46 + (a - 3) * 3 + (c - 3)];
-        }
-      }
-    } else if (e < 162) {
-      const int a = (e - 81) / 9, c = (e - 81) % 9;
-      if (!initialize && has_next) {
-        const int pa = pv_index(a), pc = pv_index(c);
-        if (pa >= 0 && pc >= 0) val = -Sigma * Dr[pc * 6 + pa] * (dv[pc] * dv[pc]);
-        else if (pa < 0 && pc < 0) val = Sigma * Dr[55 + (a - 3) * 3 + (c - 3)];
-      }
-    } else {
-      const int a = e - 162;
-      if (a < 6) val = invw * G[21 + a];
-      if (!initialize) {
-        const int pa = pv_index(a);
-        if (pa >= 0) {
-          if (has_next) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) s += Dr[k * 6 + pa] * dv[k] * Dr[36 + k];
-            val -= Sigma * s;
-          }
-          if (has_prev) val += Sigma * dv[pa] * rp[pa];
-        } else {
-          val -= Sigma * Dr[43 + (a - 3)];
-        }
-      }
-    }
-    out[e] = val;
-  }
-  if (lane == 0) out[171] = 0.0;
-}
-
-// Second version: 3 threads per frame (row blocks pos / rot / vel), 32 frames per CTA.  The frames' observation
-// and dynamics records are staged with coalesced loads into shared memory; every thread then builds three
-// complete rows of D, U and b in registers and writes them as contiguous runs (~20 warp-instructions per frame
-// instead of ~600 for the element-per-lane version above, which is kept for reference / testing).
+// 3 threads per frame (row blocks pos / rot / vel), 32 frames per CTA.  The frames' observation and dynamics
+// records are staged with coalesced loads into shared memory; every thread then builds three complete rows of
+// D, U and b in registers and writes them as contiguous runs.  Used by the partitioned / frame-window sharded
+// solves and by the diagnostics; the Monte-Carlo path builds its columns inside the sweep (kernels_chain.cu).
 constexpr int kSysFrames = 32;
 constexpr int kSysStride = VS_GREC + VS_DREC + 7;     // 99 doubles: odd stride => conflict-free row access
 constexpr int kSysOut = VS_SREC + 1;                  // 173: odd stride of the staged output records
@@ -471,20 +396,14 @@ __global__ void __launch_bounds__(96) k_system_rows(int64_t T, const int32_t* __
 int launch_system_build(vinsat_batch* b, int initialize, double Sigma, double vel_coeff) {
   vinsat_ctx* ctx = b->ctx;
   if (b->T == 0) return VINSAT_OK;
-  static const bool legacy = getenv("VINSAT_SYSTEM_LEGACY") != nullptr;
-  if (legacy) {
-    VS_LAUNCH(ctx, F_SYSTEM, k_system, ceil_div(b->T, 8), 256, 0, b->T, b->gap, b->fprob, b->wmax, b->grec, b->drec,
-              initialize, Sigma, vel_coeff, b->srec);
-  } else {
-    const int smem = kSysFrames * (kSysStride + kSysOut) * (int)sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-      VS_CUDA(ctx, cudaFuncSetAttribute(k_system_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
-    VS_LAUNCH(ctx, F_SYSTEM, k_system_rows, ceil_div(b->T, kSysFrames), 96, smem, b->T, b->gap, b->fprob, b->wmax,
-              b->grec, b->drec, initialize, Sigma, vel_coeff, b->srec);
+  const int smem = kSysFrames * (kSysStride + kSysOut) * (int)sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    VS_CUDA(ctx, cudaFuncSetAttribute(k_system_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
   }
+  VS_LAUNCH(ctx, F_SYSTEM, k_system_rows, ceil_div(b->T, kSysFrames), 96, smem, b->T, b->gap, b->fprob, b->wmax,
+            b->grec, b->drec, initialize, Sigma, vel_coeff, b->srec);
   return VINSAT_OK;
 }
 
