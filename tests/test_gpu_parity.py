@@ -146,6 +146,14 @@ def test_ba_ragged_batch_tracks_reference(ctx):
     _run_batch_vs_golden(ctx, BA_CASES)
 
 
+def test_ba_two_sided_fused_sweep_tracks_reference(ctx, monkeypatch):
+    """The same 20 iterations through the Monte-Carlo solver path (two chains per problem meeting at the middle frame,
+    normal equations assembled inside the sweep), which batches of >= 259 problems take: forced here by asking for one
+    segment per problem.  States / lamda schedule / trial counts / last Hessian against the REFERENCE's history."""
+    monkeypatch.setenv("VINSAT_SEG_LEN", "1000000")
+    _run_batch_vs_golden(ctx, BA_CASES)
+
+
 def test_system_blocks_exact_inputs(ctx):
     """First iteration from identical inputs: residuals bit-exact, weights / blocks / step at 1e-9."""
     pr = synth.make_problem(21, 50, 12, conf_lo=0.8)

@@ -34,10 +34,15 @@ def test_pipelined_solves_equal_plain_batch(ctx):
         assert np.array_equal(r, x)
 
 
+@pytest.mark.parametrize("two_sided", [True, False])
 @pytest.mark.parametrize("lengths", [(1, 2, 3), (4, 5, 7, 8), (31, 32, 33), (2, 200, 3, 101)])
-def test_two_sided_sweep_ragged_lengths(ctx, lengths):
-    """one full (non-initialize) BA iteration on problems of ragged lengths: the LM step of the two-sided sweep
-    solves the same block-tridiagonal system as the oracle's banded solve."""
+def test_two_sided_sweep_ragged_lengths(ctx, monkeypatch, lengths, two_sided):
+    """one full (non-initialize) BA iteration on problems of ragged lengths: the LM step solves the same
+    block-tridiagonal system as a dense LAPACK solve.  two_sided=True forces the Monte-Carlo path (two chains per
+    problem meeting at the middle frame, columns assembled inside the sweep) that batches of >= 259 problems take;
+    False leaves the small-batch policy (partitioned sweep, materialised system)."""
+    if two_sided:
+        monkeypatch.setenv("VINSAT_SEG_LEN", "1000000")        # one segment per problem => not partitioned
     prs = [synth.make_problem(900 + i, T, 6) for i, T in enumerate(lengths)]
     b = _lib.Batch(ctx, _lib.concat_problems(prs))
     lam, ntr = b.ba_iterate(12, 1e-4, initialize=False)
