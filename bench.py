@@ -10,7 +10,7 @@ One "step" = one batched OD solve (streaming_version's schedule on one window, o
 synthetic OD problems x 1000 frames x 10 landmark observations per frame on each GPU (weak scaling:
 problems are independent, no data-path collective).  `value` times the step with inputs resident in HBM;
 `e2e` times the same step through the public API with pinned HOST buffers (H2D of every input and D2H of
-the solved states inside the timed region).  Prints ONE JSON line on rank 0.
+the solved states inside the timed region, three solves in flight).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -273,7 +273,7 @@ def run_gpu(args):
     e2e_dev_s, e2e_serial_wall_s = timed(step_e2e, args.steps)
     e2e_serial_value = world * P * args.steps / e2e_serial_wall_s
     from vinsat_b200.pipeline import PipelinedSolver
-    depth = 2
+    depth = int(os.environ.get("VINSAT_BENCH_DEPTH", "3"))      # solves in flight (measured: 2 -> 23.8 k, 3 -> 25.2 k solves/s)
     pipe = PipelinedSolver(local, pinned, depth=depth)
     outs = [torch.empty((batch.T, 10), dtype=torch.float64).pin_memory() for _ in range(depth)]
     n_jobs = max(args.steps, depth)

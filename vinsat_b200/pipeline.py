@@ -1,4 +1,5 @@
-"""Host-side pipelining of batched OD solves: `depth` batches in flight on one GPU.
+"""Host-side pipelining of batched OD solves: `depth` batches in flight on one GPU (default 3: measured 17.6 k
+solves/s one at a time, 23.8 k with two in flight, 25.2 k with three, 26.0 k with inputs resident).
 
 One `vinsat_batch_od_solve` keeps the GPU busy for tens of milliseconds while the PCIe copy engines idle, and a
 `vinsat_batch_upload` does the opposite.  `PipelinedSolver` owns `depth` (context, stream, device batch) slots,
@@ -14,7 +15,7 @@ from . import _lib
 
 
 class PipelinedSolver:
-    def __init__(self, device, template_arrays, depth=2):
+    def __init__(self, device, template_arrays, depth=3):
         """template_arrays: dict as `_lib.concat_problems` returns; fixes (P, T, M) and the frame offsets of every
         batch that will be pushed through this solver."""
         self.slots = []
