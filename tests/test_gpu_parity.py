@@ -199,6 +199,46 @@ def test_od_solve_matches_iterate_loop_and_oracle(ctx):
     b.close(); b2.close()
 
 
+def test_speculative_od_solve_equals_iterate_loop_with_lm_rejections(ctx, monkeypatch):
+    """vinsat_batch_od_solve on the Monte-Carlo path enqueues the head of iteration i+1 before it knows whether
+    iteration i needed more than one LM trial (device-side gate).  The reference goldens include a noisy case whose LM
+    loop REJECTS first trials, so both the hit and the miss branch of the speculation run: the result must equal
+    the per-iteration loop (no speculation) bit for bit, twice in a row (gate state is reset), and the trial
+    counts must show that rejections happened."""
+    monkeypatch.setenv("VINSAT_SEG_LEN", "1000000")          # one segment per problem => Monte-Carlo solver path
+    monkeypatch.setenv("VINSAT_SPECULATE", "1")              # the pipeline is opt-in
+    gs = [load_golden(n) for n in BA_CASES]
+    prs = [problem_from_golden(g) for g in gs]
+    extra = synth.make_batch(3, 37, 5, seed0=400, sigma_px=6.0, pos_sigma=400.0)
+    arrays = _lib.concat_problems(prs + extra)
+    P = len(prs) + len(extra)
+    b2 = _lib.Batch(ctx, arrays)
+    lam = np.full(P, 1e-4)
+    total_trials = np.zeros(P, dtype=np.int64)
+    for it in range(20):
+        lam, ntr = b2.ba_iterate(it, lam, initialize=it < 10)
+        total_trials += ntr
+    s2 = b2.get_states()
+    assert total_trials.max() > 20, "no LM rejection in this batch: the miss branch would be untested"
+    b = _lib.Batch(ctx, arrays)
+    for _ in range(2):
+        b.upload(arrays)
+        b.od_solve(20, 10, 1e-4)
+        s1 = b.get_states()
+        assert np.array_equal(s1, s2)
+    H1, H2 = b.last_hessian(), b2.last_hessian()
+    assert np.array_equal(H1, H2)
+    # odd iteration counts / a single iteration (no speculation possible) / solve after solve on the same states
+    for n_it, n_init in ((1, 1), (3, 1), (7, 2)):
+        b.upload(arrays); b2.upload(arrays)
+        b.od_solve(n_it, n_init, 1e-4)
+        lam = np.full(P, 1e-4)
+        for it in range(n_it):
+            lam, _ = b2.ba_iterate(it, lam, initialize=it < n_init)
+        assert np.array_equal(b.get_states(), b2.get_states()), (n_it, n_init)
+    b.close(); b2.close()
+
+
 def test_batch_upload_reuses_allocation(ctx):
     prs = synth.make_batch(2, 20, 5, seed0=7)
     prs2 = synth.make_batch(2, 20, 5, seed0=9)

@@ -373,22 +373,25 @@ static int wait_flag(vinsat_batch* b) {
 }
 
 // One LM trial: solve, retract, trial residuals, accept test, copy of the "still active" counter to the host.
-static int issue_trial(vinsat_batch* b, int initialize, int mode, double Sigma, double quat_coeff, double vel_coeff) {
+static int issue_trial(vinsat_batch* b, int initialize, int mode, double Sigma, double quat_coeff, double vel_coeff,
+                       int32_t* h_dst = nullptr) {
   vinsat_ctx* ctx = b->ctx;
   VS_TRY(launch_solve_retract(b, initialize));
   VS_TRY(launch_obs_trial(b));
   if (!initialize)
     VS_TRY(launch_dyn_trial(ctx, b->n_pairs, b->dyn_order, b->st_new, b->crot, b->gap, b->active, b->fprob,
-                            quat_coeff, vel_coeff, mode, b->e_dyn, nullptr));
-  VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, sizeof(int32_t), ctx->stream));
+                            quat_coeff, vel_coeff, mode, b->e_dyn, nullptr, b->gate_arg));
+  if (b->gate_arg) VS_TRY(launch_gated_zero(b, nullptr, 0, b->flags, 1));
+  else VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, sizeof(int32_t), ctx->stream));
   VS_TRY(launch_accept(b, initialize, Sigma));
-  VS_CUDA(ctx, cudaMemcpyAsync(b->h_flags, b->flags, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (b->gate_arg) VS_TRY(launch_gate_publish(b));
+  VS_CUDA(ctx, cudaMemcpyAsync(h_dst ? h_dst : b->h_flags, b->flags, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   return VINSAT_OK;
 }
 
 // Linearisation + first trial of one BA() call (everything that does not depend on a host decision).
 static int issue_iteration_head(vinsat_batch* b, int iter, int initialize, int mode, const double* lam_dev_in,
-                                bool have_residuals) {
+                                bool have_residuals, int32_t* h_dst = nullptr) {
   vinsat_ctx* ctx = b->ctx;
   const double quat_coeff = 100.0, vel_coeff = 100.0;                                  // BA_filtering.py:11-12
   const double alpha = std::min(std::max(1.0 - (2.0 * ((double)iter / 5.0) - 1.0), 1.0), 2.0);   // :22
@@ -398,8 +401,9 @@ static int issue_iteration_head(vinsat_batch* b, int iter, int initialize, int m
   VS_TRY(launch_select_median(b));
   VS_TRY(launch_obs_assemble(b, alpha));
   if (!initialize) {
-    VS_TRY(launch_dynamics_stm(ctx, b->n_pairs, b->dyn_order, b->st, b->gap, vel_coeff, mode, b->drec, nullptr, b->mrec));
-    VS_TRY(launch_quat_terms(ctx, b->T, b->st, b->crot, b->gap, quat_coeff, b->drec));
+    VS_TRY(launch_dynamics_stm(ctx, b->n_pairs, b->dyn_order, b->st, b->gap, vel_coeff, mode, b->drec, nullptr, b->mrec,
+                               b->gate_arg));
+    VS_TRY(launch_quat_terms(ctx, b->T, b->st, b->crot, b->gap, quat_coeff, b->drec, b->gate_arg));
   }
   // initialize phase: block-diagonal system, solved straight from the observation records (k_solve_init);
   // the full records are only materialised on demand (last_hessian / debug_fetch).
@@ -407,7 +411,7 @@ static int issue_iteration_head(vinsat_batch* b, int iter, int initialize, int m
   // build); the partitioned sweep and the diagnostics read the materialised records.
   if (!initialize && !b->fused_system) VS_TRY(launch_system_build(b, 0, Sigma, vel_coeff));
   VS_TRY(launch_init_residual(b, initialize, Sigma, 0.0, lam_dev_in));
-  return issue_trial(b, initialize, mode, Sigma, quat_coeff, vel_coeff);
+  return issue_trial(b, initialize, mode, Sigma, quat_coeff, vel_coeff, h_dst);
 }
 
 // One BA() call for every problem of the batch; lam_dev_in holds lamda_init per problem on the device.
@@ -506,7 +510,115 @@ int vinsat_batch_od_solve(vinsat_batch* b, int num_iters, int n_init, double lam
   if (!h) return set_error(ctx, VINSAT_ENOMEM, "pinned scratch failed");
   for (int64_t p = 0; p < b->P; p++) h[p] = lamda_init;
   VS_CUDA(ctx, cudaMemcpyAsync(b->lam_next, h, b->P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  for (int it = 0; it < num_iters; it++) VS_TRY(ba_iterate_device(b, it, it < n_init ? 1 : 0, mode, b->lam_next));
+  // Speculative pipeline (Monte-Carlo path): the head of iteration it+1 is enqueued BEFORE the host learns whether
+  // iteration it's LM loop ended with its first trial.  Every kernel of a head carries the device gate word: the
+  // first trial publishes the number of still-active problems into it, and while it is non-zero the kernels behind
+  // it return at once.  In the common case the GPU never waits for the host; otherwise the host finishes the loop
+  // with ungated trials, clears the gate and enqueues the head again.
+  // OPT-IN (VINSAT_SPECULATE=1).  Measured on B200: it removes the 20 host round trips per solve, which costs 0.3 ms
+  // per solve on a host whose round trips are already short (3 extra tiny launches per iteration) and did not change
+  // the 8-GPU result (the ranks that run slow there stay slow), so the default is the plain loop.
+  const bool no_spec = getenv("VINSAT_SPECULATE") == nullptr;      // read per call (tests switch it)
+  const bool smem_select = 2 * b->max_obs_per_problem > 0 && 2 * b->max_obs_per_problem <= 24000 &&
+                           getenv("VINSAT_SELECT_GLOBAL") == nullptr;
+  if (no_spec || ctx->timing || b->window || b->partitioned || !smem_select || num_iters < 2) {
+    for (int it = 0; it < num_iters; it++) VS_TRY(ba_iterate_device(b, it, it < n_init ? 1 : 0, mode, b->lam_next));
+    return VINSAT_OK;
+  }
+  const double quat_coeff = 100.0, vel_coeff = 100.0;
+  static const bool no_fuse = getenv("VINSAT_NO_FUSED_SYSTEM") != nullptr || getenv("VINSAT_ONE_SIDED_SWEEP") != nullptr;
+  auto sigma_of = [](int it) { const double it1 = (double)it + 1.0; return std::min(10000.0 * it1 * it1, 1000000.0); };
+  bool swapped_r = false;
+  auto begin_iter = [&](int it) {                    // host-side state of ba_iterate_device's prologue
+    const int init = it < n_init ? 1 : 0;
+    swapped_r = b->r_valid;
+    if (swapped_r) std::swap(b->r, b->r_next);
+    b->fused_system = !init && !no_fuse;
+    b->srec_valid = !init && !b->fused_system;
+    b->last_sigma = b->cur_sigma = sigma_of(it);
+    b->cur_vc = vel_coeff;
+    return swapped_r;
+  };
+  auto end_iter = [&](int it) {                      // ... and of its epilogue
+    std::swap(b->st, b->st_new);
+    b->r_valid = true;
+    b->have_iter = true;
+    b->last_initialize = it < n_init ? 1 : 0;
+  };
+  b->gate = b->flags + 3;
+  VS_CUDA(ctx, cudaMemsetAsync(b->gate, 0, sizeof(int32_t), ctx->stream));
+  b->gate_arg = b->gate;
+  volatile int32_t* ring = b->h_flags + 2;
+  auto fail = [&](int rc) { b->gate_arg = nullptr; return rc; };
+  {
+    const bool had = begin_iter(0);
+    ring[0] = -1;
+    const int rc = issue_iteration_head(b, 0, 0 < n_init ? 1 : 0, mode, b->lam_next, had, b->h_flags + 2);
+    if (rc != VINSAT_OK) return fail(rc);
+  }
+  for (int it = 0; it < num_iters; it++) {
+    const int init = it < n_init ? 1 : 0;
+    const bool spec = it + 1 < num_iters;
+    const bool r_valid_before = b->r_valid;
+    bool had_next = false;
+    if (spec) {
+      end_iter(it);
+      had_next = begin_iter(it + 1);
+      ring[(it + 1) & 1] = -1;
+      const int rc = issue_iteration_head(b, it + 1, it + 1 < n_init ? 1 : 0, mode, b->lam_next, had_next,
+                                          b->h_flags + 2 + ((it + 1) & 1));
+      if (rc != VINSAT_OK) return fail(rc);
+    }
+    {                                                 // wait for iteration it's first-trial counter
+      int64_t spins = 0;
+      while (ring[it & 1] == -1 && ++spins < 400000000ll) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+      }
+      if (ring[it & 1] == -1) {
+        const cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) { b->gate_arg = nullptr; VS_CUDA(ctx, ce); }
+      }
+    }
+    if (ring[it & 1] == 0) {
+      if (!spec) end_iter(it);
+      continue;
+    }
+    // some problem's LM loop goes on: the head enqueued behind it is skipped on the device
+    {
+      const cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+      if (ce != cudaSuccess) { b->gate_arg = nullptr; VS_CUDA(ctx, ce); }
+    }
+    if (spec) {                                       // take back the host-side effects of the skipped head
+      if (had_next) std::swap(b->r, b->r_next);
+      std::swap(b->st, b->st_new);
+      b->r_valid = r_valid_before;
+      b->fused_system = !init && !no_fuse;
+      b->srec_valid = !init && !b->fused_system;
+      b->last_sigma = b->cur_sigma = sigma_of(it);
+    }
+    b->gate_arg = nullptr;                            // the remaining trials of iteration it run ungated
+    for (int trial = 1; trial < 16; trial++) {
+      b->h_flags[0] = -1;
+      int rc = issue_trial(b, init, mode, sigma_of(it), quat_coeff, vel_coeff);
+      if (rc == VINSAT_OK) rc = wait_flag(b);
+      if (rc != VINSAT_OK) return rc;
+      if (b->h_flags[0] == 0) break;
+    }
+    VS_CUDA(ctx, cudaMemsetAsync(b->gate, 0, sizeof(int32_t), ctx->stream));
+    b->gate_arg = b->gate;
+    end_iter(it);
+    if (spec) {
+      had_next = begin_iter(it + 1);
+      ring[(it + 1) & 1] = -1;
+      const int rc = issue_iteration_head(b, it + 1, it + 1 < n_init ? 1 : 0, mode, b->lam_next, had_next,
+                                          b->h_flags + 2 + ((it + 1) & 1));
+      if (rc != VINSAT_OK) return fail(rc);
+    }
+    // invariant restored: at the top of pass it+1 the head of iteration it+1 is in flight
+  }
+  b->gate_arg = nullptr;
   return VINSAT_OK;
 }
 

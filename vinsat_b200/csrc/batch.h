@@ -81,7 +81,9 @@ struct vinsat_batch {
   unsigned long long* sel_rank = nullptr;    // [P]
   unsigned int* sel_hist = nullptr;          // [P][2048]
   int32_t* flags = nullptr;    // [4]: 0 = n_active, 1 = index error
-  int32_t* h_flags = nullptr;  // pinned mirror
+  int32_t* h_flags = nullptr;  // pinned mirror ([0]: trial counter; [2], [3]: ring for the speculative pipeline)
+  int32_t* gate = nullptr;     // device word: != 0 while an LM loop behind speculatively launched work is unfinished
+  const int32_t* gate_arg = nullptr;   // what the launches of the moment pass to their kernels (null = ungated)
   // ---- frame-window sharded long arc (longarc.cu): this batch holds ONE problem = owned frames + ghosts ----
   bool window = false;
   int64_t own_lo = 0, own_hi = 0;     // owned local frames [own_lo, own_hi); ghosts (if any) at own_lo-1 / own_hi

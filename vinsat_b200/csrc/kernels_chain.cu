@@ -226,6 +226,7 @@ struct ChainArgs {
   const int32_t* ch_mid = nullptr;     // middle element per chain (or -1: empty problem), or null
   double* mid = nullptr;               // [n_chains][VS_MIDREC]  Lo W (row-major 81) | Lo y (9) of the chain's last element
   int fused = 0;                       // 1: rec is null, columns come from `fs` (fused system build)
+  const int32_t* gate = nullptr;       // speculation gate: the kernel returns at once while *gate != 0
   FusedSrc fs;
 };
 constexpr int VS_MIDREC = 96;
@@ -335,6 +336,7 @@ constexpr int kF3Warps = 1;
 template <bool SPIKE, bool FUSED>
 __global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
   constexpr int NS = SPIKE ? 3 : 2;
+  if (A.gate && *A.gate) return;
   __shared__ __align__(16) double s_col[kF3Warps][kCPW][2][3][kMS];
   __shared__ __align__(16) double s_M[kF3Warps][kCPW][9 * kMS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -534,6 +536,7 @@ static int launch_forward(vinsat_ctx* ctx, const ChainArgs& A) {
 constexpr int kRing = 8;
 
 __global__ void __launch_bounds__(128) k_chain_backward(ChainArgs A) {
+  if (A.gate && *A.gate) return;
   __shared__ __align__(16) double s_ring[4][kRing][96];
   __shared__ __align__(16) double s_col[4][2][3][kMS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -884,6 +887,7 @@ int launch_chain_solve(vinsat_batch* b) {
       A.n_chains = (int)(2 * b->P);
       A.ch_a = b->bb_a; A.ch_b = b->bb_e; A.ch_left = nullptr; A.ch_prob = b->bb_prob;
       A.ch_dir = b->bb_dir; A.ch_mid = b->bb_mid; A.mid = b->midrec;
+      A.gate = b->gate_arg;
       if (b->fused_system) {
         A.fused = 1; A.rec = nullptr;
         A.fs.grec = b->grec; A.fs.drec = b->drec; A.fs.mrec = b->mrec; A.fs.gap = b->gap; A.fs.wmax = b->wmax;

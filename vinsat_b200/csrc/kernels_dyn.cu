@@ -18,7 +18,8 @@ __global__ void __launch_bounds__(128) k_dynamics_stm(int64_t n_pairs, const int
                                                       const double* __restrict__ st,
                                                       const int32_t* __restrict__ gap, double vel_coeff, int mode,
                                                       double* __restrict__ drec, double* __restrict__ x_pred,
-                                                      double* __restrict__ mrec) {
+                                                      double* __restrict__ mrec, const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int half = (int)(t & 1);
   const bool live = (t >> 1) < n_pairs;
@@ -104,11 +105,12 @@ __global__ void __launch_bounds__(128) k_dynamics_stm(int64_t n_pairs, const int
 }
 
 int launch_dynamics_stm(vinsat_ctx* ctx, int64_t n_pairs, const int32_t* order, const double* st,
-                        const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred, double* mrec) {
+                        const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred, double* mrec,
+                        const int32_t* gate) {
   if (n_pairs == 0) return VINSAT_OK;
   static const int th = getenv("VINSAT_DYN_THREADS") ? atoi(getenv("VINSAT_DYN_THREADS")) : 32;   // 198 registers: 32-thread CTAs pack 10 warps per SM (128-thread CTAs: 8)
   VS_LAUNCH(ctx, F_DYNAMICS, k_dynamics_stm, ceil_div(n_pairs * 2, th), th, 0, n_pairs, order, st, gap, vel_coeff,
-            mode, drec, x_pred, mrec);
+            mode, drec, x_pred, mrec, gate);
   return VINSAT_OK;
 }
 
@@ -131,7 +133,8 @@ constexpr int kQtOut = 23;      // 22 outputs, odd pitch
 __global__ void __launch_bounds__(kQtFrames) k_quat_terms(int64_t T, const double* __restrict__ st,
                                                           const double* __restrict__ crot,
                                                           const int32_t* __restrict__ gap, double c,
-                                                          double* __restrict__ drec) {
+                                                          double* __restrict__ drec, const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   __shared__ double s_q[(kQtFrames + 2) * 4];      // quaternion of frames f0-1 .. f0+128
   __shared__ double s_r[(kQtFrames + 1) * 4];      // cum rotation of frames f0-1 .. f0+127
   __shared__ int32_t s_gap[kQtFrames + 1];         // gap of frames f0-1 .. f0+127
@@ -206,9 +209,9 @@ __global__ void __launch_bounds__(kQtFrames) k_quat_terms(int64_t T, const doubl
 }
 
 int launch_quat_terms(vinsat_ctx* ctx, int64_t T, const double* st, const double* crot, const int32_t* gap,
-                      double quat_coeff, double* drec) {
+                      double quat_coeff, double* drec, const int32_t* gate) {
   if (T == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_QUAT, k_quat_terms, ceil_div(T, 128), 128, 0, T, st, crot, gap, quat_coeff, drec);
+  VS_LAUNCH(ctx, F_QUAT, k_quat_terms, ceil_div(T, 128), 128, 0, T, st, crot, gap, quat_coeff, drec, gate);
   return VINSAT_OK;
 }
 
@@ -220,7 +223,9 @@ __global__ void __launch_bounds__(128) k_dyn_trial(int64_t n_pairs, const int32_
                                                    const int32_t* __restrict__ gap,
                                                    const int32_t* __restrict__ active,
                                                    const int32_t* __restrict__ fprob, double qc, double vc, int mode,
-                                                   double* __restrict__ e_dyn, double* __restrict__ r7_out) {
+                                                   double* __restrict__ e_dyn, double* __restrict__ r7_out,
+                                                   const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= n_pairs) return;
   const int64_t f = order ? order[j] : j;
@@ -248,10 +253,11 @@ __global__ void __launch_bounds__(128) k_dyn_trial(int64_t n_pairs, const int32_
 
 int launch_dyn_trial(vinsat_ctx* ctx, int64_t n_pairs, const int32_t* order, const double* st,
                      const double* crot, const int32_t* gap, const int32_t* active, const int32_t* fprob,
-                     double quat_coeff, double vel_coeff, int mode, double* e_dyn, double* r7_out) {
+                     double quat_coeff, double vel_coeff, int mode, double* e_dyn, double* r7_out,
+                     const int32_t* gate) {
   if (n_pairs == 0) return VINSAT_OK;
   VS_LAUNCH(ctx, F_TRIAL, k_dyn_trial, ceil_div(n_pairs, 128), 128, 0, n_pairs, order, st, crot, gap, active, fprob,
-            quat_coeff, vel_coeff, mode, e_dyn, r7_out);
+            quat_coeff, vel_coeff, mode, e_dyn, r7_out, gate);
   return VINSAT_OK;
 }
 

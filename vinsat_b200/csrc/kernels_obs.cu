@@ -449,7 +449,9 @@ __global__ void __launch_bounds__(32, 9) k_obs_assemble_2pass(int64_t T, int64_t
                                                               const double* __restrict__ intr,
                                                               const double* __restrict__ c_obs, WeightParams wp,
                                                               double* __restrict__ wu_out, double* __restrict__ grec,
-                                                              unsigned long long* __restrict__ wmax) {
+                                                              unsigned long long* __restrict__ wmax,
+                                                              const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   extern __shared__ __align__(16) double sm2[];
   double* tile = sm2;                                       // [k2pSlots][k2pChunk]
   double* fdat = sm2 + k2pSlots * k2pChunk;                 // [32][k2pFrameRec]
@@ -614,7 +616,12 @@ int launch_obs_assemble(vinsat_batch* b, double alpha) {
   wp.ex = alpha / 2.0 - 1.0;
   wp.alpha_is_two = (wp.ex == 0.0) ? 1 : 0;
   wp.ex_is_mhalf = (wp.ex == -0.5) ? 1 : 0;
-  VS_CUDA(ctx, cudaMemsetAsync(b->wmax, 0, b->P * sizeof(unsigned long long), ctx->stream));
+  if (b->gate_arg) {
+    int rc = launch_gated_zero(b, b->wmax, b->P, nullptr, 0);
+    if (rc != VINSAT_OK) return rc;
+  } else {
+    VS_CUDA(ctx, cudaMemsetAsync(b->wmax, 0, b->P * sizeof(unsigned long long), ctx->stream));
+  }
   if (b->T == 0) return VINSAT_OK;
   static int variant = getenv("VINSAT_ASM_VARIANT") ? atoi(getenv("VINSAT_ASM_VARIANT")) : 0;
   if (variant == 32) {            // thread-per-frame walk (kept for comparison)
@@ -635,7 +642,7 @@ int launch_obs_assemble(vinsat_batch* b, double alpha) {
     attr_set = true;
   }
   VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_2pass, ceil_div(b->T, 32), 32, smem, b->T, b->M, b->obs_start, b->oframe,
-            b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
+            b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax, b->gate_arg);
   return VINSAT_OK;
 }
 
@@ -646,7 +653,9 @@ __global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const i
                                                    const int32_t* __restrict__ active, const double* __restrict__ X,
                                                    const double* __restrict__ uv, const double* __restrict__ wu,
                                                    const double* __restrict__ st, const double* __restrict__ intr,
-                                                   double* __restrict__ e_obs, double* __restrict__ r_next) {
+                                                   double* __restrict__ e_obs, double* __restrict__ r_next,
+                                                   const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   const int gl = threadIdx.x & (kGroup - 1);
   const int64_t f = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kGroup;
   const bool valid = f < T;
@@ -678,10 +687,10 @@ int launch_obs_trial(vinsat_batch* b) {
   if (b->T == 0) return VINSAT_OK;
   if (b->M <= 16 * b->T) {       // sparse frames: 2 lanes per frame (measured best of 1/2/4/8 at K = 10)
     VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<2>, ceil_div(b->T * 2, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
-              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
+              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next, b->gate_arg);
   } else {
     VS_LAUNCH(ctx, F_TRIAL, k_obs_trial<8>, ceil_div(b->T * 8, 256), 256, 0, b->T, b->M, b->obs_start, b->fprob,
-              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next);
+              b->active, b->X, b->uv, b->wu, b->st_new, b->intr, b->e_obs, b->r_next, b->gate_arg);
   }
   return VINSAT_OK;
 }

@@ -96,7 +96,9 @@ constexpr int kSelThreads = 1024;
 constexpr int kSelCand = 2048;      // candidate list: keys that share the digits found so far
 
 __global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const int64_t* __restrict__ obs_off,
-                                                             const double* __restrict__ r, double* __restrict__ c_obs) {
+                                                             const double* __restrict__ r, double* __restrict__ c_obs,
+                                                             const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   extern __shared__ __align__(16) unsigned long long sel_keys[];      // [n] keys, then [kSelCand] candidates
   __shared__ unsigned int hist[kSelBins];
   __shared__ unsigned int wsum[32];
@@ -255,7 +257,8 @@ int launch_select_median(vinsat_batch* b) {
       VS_CUDA(ctx, cudaFuncSetAttribute(k_select_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_smem = smem;
     }
-    VS_LAUNCH(ctx, F_SELECT, k_select_smem, (unsigned)b->P, kSelThreads, smem, b->M, b->d_obs_off, b->r, b->c_obs);
+    VS_LAUNCH(ctx, F_SELECT, k_select_smem, (unsigned)b->P, kSelThreads, smem, b->M, b->d_obs_off, b->r, b->c_obs,
+              b->gate_arg);
     return VINSAT_OK;
   }
   int rc = launch_select_begin(b, -1);
@@ -445,7 +448,9 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_init_residual(int P, 
                                                        const double* __restrict__ drec, int initialize,
                                                        double sqrt_sigma, const double* __restrict__ lam_in,
                                                        double* __restrict__ lam, double* __restrict__ init_res,
-                                                       int32_t* __restrict__ active, int32_t* __restrict__ ntrials) {
+                                                       int32_t* __restrict__ active, int32_t* __restrict__ ntrials,
+                                                       const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   __shared__ double s_part[32];
   const int p = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kPT);
   const int lane = threadIdx.x % kPT;
@@ -476,11 +481,11 @@ int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double, 
   if (b->T > 4096 * b->P) {              // long arcs: one CTA per problem
     VS_LAUNCH(ctx, F_ACCEPT, k_init_residual<1024>, (unsigned)b->P, 1024, 0, (int)b->P, b->d_frame_off,
               b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
-              b->active, b->ntrials);
+              b->active, b->ntrials, b->gate_arg);
   } else {
     VS_LAUNCH(ctx, F_ACCEPT, k_init_residual<32>, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off,
               b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
-              b->active, b->ntrials);
+              b->active, b->ntrials, b->gate_arg);
   }
   return VINSAT_OK;
 }
@@ -494,7 +499,9 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_accept(int P, const i
                                                 int initialize, double sqrt_sigma,
                                                 const double* __restrict__ init_res, double* __restrict__ lam,
                                                 double* __restrict__ lam_next, int32_t* __restrict__ active,
-                                                int32_t* __restrict__ ntrials, int32_t* __restrict__ flags) {
+                                                int32_t* __restrict__ ntrials, int32_t* __restrict__ flags,
+                                                const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   __shared__ double s_part[32];
   const int p = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kPT);
   const int lane = threadIdx.x % kPT;
@@ -532,11 +539,11 @@ int launch_accept(vinsat_batch* b, int initialize, double Sigma) {
   if (b->T > 4096 * b->P) {
     VS_LAUNCH(ctx, F_ACCEPT, k_accept<1024>, (unsigned)b->P, 1024, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
               b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
-              b->ntrials, b->flags);
+              b->ntrials, b->flags, b->gate_arg);
   } else {
     VS_LAUNCH(ctx, F_ACCEPT, k_accept<32>, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
               b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
-              b->ntrials, b->flags);
+              b->ntrials, b->flags, b->gate_arg);
   }
   return VINSAT_OK;
 }
@@ -549,7 +556,8 @@ __global__ void __launch_bounds__(128) k_solve_init(int64_t T, const int32_t* __
                                                     const double* __restrict__ lam,
                                                     const unsigned long long* __restrict__ wmax,
                                                     const double* __restrict__ grec, double* __restrict__ delta,
-                                                    double* __restrict__ lam32_last) {
+                                                    double* __restrict__ lam32_last, const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   const int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (f >= T) return;
   const int p = fprob[f];
@@ -611,7 +619,8 @@ __global__ void __launch_bounds__(128) k_solve_init(int64_t T, const int32_t* __
 __global__ void __launch_bounds__(128) k_retract(int64_t T, const int32_t* __restrict__ fprob,
                                                  const int32_t* __restrict__ active,
                                                  const double* __restrict__ st, const double* __restrict__ delta,
-                                                 double* __restrict__ st_new) {
+                                                 double* __restrict__ st_new, const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   __shared__ double s_st[128 * 10 + 1];
   __shared__ double s_d[128 * 9];
   __shared__ int s_act[128];
@@ -641,7 +650,7 @@ int launch_solve_init_only(vinsat_batch* b) {
   vinsat_ctx* ctx = b->ctx;
   if (b->T == 0) return VINSAT_OK;
   VS_LAUNCH(ctx, F_SOLVE_INIT, k_solve_init, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->lam, b->wmax,
-            b->grec, b->delta, b->lam32_last);
+            b->grec, b->delta, b->lam32_last, b->gate_arg);
   return VINSAT_OK;
 }
 
@@ -649,7 +658,7 @@ int launch_retract_only(vinsat_batch* b) {
   vinsat_ctx* ctx = b->ctx;
   if (b->T == 0) return VINSAT_OK;
   VS_LAUNCH(ctx, F_RETRACT, k_retract, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->st, b->delta,
-            b->st_new);
+            b->st_new, b->gate_arg);
   return VINSAT_OK;
 }
 
@@ -658,13 +667,42 @@ int launch_solve_retract(vinsat_batch* b, int initialize) {
   if (b->P == 0 || b->T == 0) return VINSAT_OK;
   if (initialize) {
     VS_LAUNCH(ctx, F_SOLVE_INIT, k_solve_init, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->lam, b->wmax,
-              b->grec, b->delta, b->lam32_last);
+              b->grec, b->delta, b->lam32_last, b->gate_arg);
   } else {
     int rc = launch_chain_solve(b);
     if (rc != VINSAT_OK) return rc;
   }
   VS_LAUNCH(ctx, F_RETRACT, k_retract, ceil_div(b->T, 128), 128, 0, b->T, b->fprob, b->active, b->st, b->delta,
-            b->st_new);
+            b->st_new, b->gate_arg);
+  return VINSAT_OK;
+}
+
+// Zeroing that respects the speculation gate (a cudaMemsetAsync cannot be skipped on the device).
+__global__ void k_gated_zero(unsigned long long* __restrict__ p64, int64_t n64, int32_t* __restrict__ p32, int n32,
+                             const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n64) p64[i] = 0ull;
+  if (i < n32) p32[i] = 0;
+}
+
+int launch_gated_zero(vinsat_batch* b, unsigned long long* p64, int64_t n64, int32_t* p32, int n32) {
+  vinsat_ctx* ctx = b->ctx;
+  const int64_t n = n64 > n32 ? n64 : n32;
+  if (n <= 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_ACCEPT, k_gated_zero, ceil_div(n, 256), 256, 0, p64, n64, p32, n32, b->gate_arg);
+  return VINSAT_OK;
+}
+
+// After the first trial of a speculatively pipelined iteration: gate <- number of problems whose LM loop goes on.
+// While it is non-zero every kernel launched behind it returns at once (the host then finishes that loop).
+__global__ void k_gate_publish(int32_t* __restrict__ gate, const int32_t* __restrict__ flags) {
+  if (*gate == 0) *gate = flags[0];
+}
+
+int launch_gate_publish(vinsat_batch* b) {
+  vinsat_ctx* ctx = b->ctx;
+  VS_LAUNCH(ctx, F_ACCEPT, k_gate_publish, 1, 1, 0, b->gate, b->flags);
   return VINSAT_OK;
 }
 

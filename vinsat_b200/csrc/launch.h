@@ -25,14 +25,16 @@ int launch_soa_to_aos(vinsat_ctx* ctx, const double* soa, double* aos, int64_t n
 // ---- kernels_dyn.cu ---------------------------------------------------------------------------------
 // RK4 + STM for the pairs listed in `order` (2 threads per pair): writes Phi, r6 into drec; x_pred optional.
 int launch_dynamics_stm(vinsat_ctx* ctx, int64_t n_pairs, const int32_t* order, const double* st,
-                        const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred, double* mrec);
+                        const int32_t* gap, double vel_coeff, int mode, double* drec, double* x_pred, double* mrec,
+                        const int32_t* gate = nullptr);
 // Quaternion smoothness terms per frame: rho, qgrad, Hq_diag, Hq_off into drec.
 int launch_quat_terms(vinsat_ctx* ctx, int64_t T, const double* st, const double* crot, const int32_t* gap,
-                      double quat_coeff, double* drec);
+                      double quat_coeff, double* drec, const int32_t* gate = nullptr);
 // Trial: residual-only propagation; e_dyn[f] = sum |r_pred(f)| over the 7 components (0 where no pair).
 int launch_dyn_trial(vinsat_ctx* ctx, int64_t n_pairs, const int32_t* order, const double* st,
                      const double* crot, const int32_t* gap, const int32_t* active, const int32_t* fprob,
-                     double quat_coeff, double vel_coeff, int mode, double* e_dyn, double* r7_out);
+                     double quat_coeff, double vel_coeff, int mode, double* e_dyn, double* r7_out,
+                     const int32_t* gate = nullptr);
 int launch_chain(vinsat_ctx* ctx, int64_t n_steps, double dt, const double* state0, const double* vel0,
                  const double* omega, double* states_out);
 int launch_orbit_propagate(vinsat_ctx* ctx, int64_t n_traj, int64_t n_steps, int64_t stride, double h,
@@ -66,5 +68,9 @@ int launch_cum_rot_frames(vinsat_ctx* ctx, int64_t T, int64_t n_full, const int6
 int launch_cum_rot_prefix(vinsat_ctx* ctx, int64_t T, int64_t N, const double* omegas, double dt, double* cum);
 int launch_attitude_propagate(vinsat_ctx* ctx, int64_t n_traj, int64_t n_steps, int64_t stride, double h,
                               const double* inertia, const double* x0, double* out);
+
+// ---- speculation gate (kernels_solve.cu; see vinsat_batch_od_solve) ---------------------------------------
+int launch_gated_zero(vinsat_batch* b, unsigned long long* p64, int64_t n64, int32_t* p32, int n32);
+int launch_gate_publish(vinsat_batch* b);
 
 }  // namespace vs
