@@ -179,6 +179,18 @@ def golden_helpers():
     print("helpers saved")
 
 
+def make_mgrs_table():
+    """sim/getMGRS.py of the reference: the ordered zone table (tests/golden/mgrs_table.json)."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("ref_mgrs", "/root/reference/sim/getMGRS.py")
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    table = m.getMGRS()
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "mgrs_table.json"), "w") as f:
+        json.dump([[k] + [int(x) for x in v] for k, v in table.items()], f, separators=(",", ":"))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("ba", "all"):
@@ -186,6 +198,7 @@ if __name__ == "__main__":
         golden_long_gap()
     if what in ("helpers", "all"):
         golden_helpers()
+        make_mgrs_table()
     if what in ("indexing", "streaming", "all"):
         import make_golden_streaming  # noqa: F401  (kept separate: slower)
         make_golden_streaming.main(what)

@@ -89,3 +89,15 @@ def test_host_helpers_vs_reference_golden():
     for k in range(5):
         xa = trajgen_pipe.attitude_step(xa.copy(), 1.0)
         assert np.abs(xa - g["att_traj"][k + 1]).max() < 1e-15
+
+
+def test_mgrs_table_equals_reference_order_and_values():
+    """SatCam.get_region returns the FIRST zone containing a point, so the key order is part of the contract."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from vinsat_b200.sim.getMGRS import getMGRS
+    ref = json.load(open(os.path.join(GOLDEN, "mgrs_table.json")))
+    got = [[k] + [int(x) for x in v] for k, v in getMGRS().items()]
+    assert got == ref and len(got) == 1197
+

@@ -1,24 +1,28 @@
-"""MGRS 6 x 8 degree grid lookup (sim/getMGRS.py:5-30)."""
-import numpy as np
+"""MGRS grid-zone lookup used by SatCam.get_region: zone id -> (west, south, east, north) in degrees.
+
+Same table as the reference's ``sim/getMGRS.py:5-30`` (and the same key ORDER, band by band from 80 S, zones west to
+east inside a band: `get_region` returns the first zone whose closed box contains a point, so the order decides ties
+on zone borders).  Built from the definition of the grid rather than by patching a regular grid afterwards.
+"""
+
+# 8-degree latitude bands from 80 S upwards (I and O are not used); the last band, X, is 12 degrees tall (72..84 N)
+_BANDS = "CDEFGHJKLMNPQRSTUVWX"
+# Norway (band V) and Svalbard (band X) exceptions: zone -> (west, east); a missing zone is None
+_IRREGULAR = {
+    "V": {31: (0, 3), 32: (3, 12)},
+    "X": {31: (0, 9), 32: None, 33: (9, 21), 34: None, 35: (21, 33), 36: None, 37: (33, 42)},
+}
 
 
 def getMGRS():
-    LON_STEP, LAT_STEP = 6, 8
-    lons = np.arange(-180, 180, LON_STEP)
-    lats = np.arange(-80, 80, LAT_STEP)
-    lon_labels = np.arange(1, 61)
-    lat_labels = ['C', 'D', 'E', 'F', 'G', 'H', 'J', 'K', 'L', 'M', 'N', 'P', 'Q', 'R', 'S', 'T', 'U', 'V', 'W', 'X']
     grid = {}
-    for i in range(len(lats)):
-        for j in range(len(lons)):
-            grid[str(lon_labels[j]).zfill(2) + lat_labels[i]] = (lons[j], lats[i], lons[j] + LON_STEP, lats[i] + LAT_STEP)
-    for i in lon_labels:
-        grid[str(i).zfill(2) + 'X'] = (lons[i - 1], 72, lons[i - 1] + LON_STEP, 84)
-    grid['31V'] = (0, 56, 3, 64)
-    grid['32V'] = (3, 56, 12, 64)
-    grid['31X'] = (0, 72, 9, 84)
-    grid['33X'] = (9, 72, 21, 84)
-    grid['35X'] = (21, 72, 33, 84)
-    grid['37X'] = (33, 72, 42, 84)
-    del grid['32X'], grid['34X'], grid['36X']
+    for k, band in enumerate(_BANDS):
+        south = 8 * k - 80
+        north = 84 if band == "X" else south + 8
+        special = _IRREGULAR.get(band, {})
+        for zone in range(1, 61):
+            west_east = special.get(zone, (6 * zone - 186, 6 * zone - 180))
+            if west_east is None:
+                continue
+            grid["%02d%s" % (zone, band)] = (west_east[0], south, west_east[1], north)
     return grid
