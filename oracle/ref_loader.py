@@ -89,3 +89,46 @@ def load():
     ns = types.SimpleNamespace(BA_utils=BA_utils, BA_filtering=BA_filtering,
                                trajgen_pipe=trajgen_pipe, od_pipe=od_pipe, est_dir=est)
     return ns
+
+
+def load_satcam():
+    """Import the UNMODIFIED ``sim/SatCam.py`` (and ``sim/orbit_gen.py``).  Its geometry is pure NumPy; the
+    modules it imports but that are absent here (astropy, rasterio, pyproj) are only reached by
+    ``get_corner_lonlats`` (astropy, SatCam.py:181), ``lonlat_to_pixel_coords`` (pyproj, :194-199) and the image
+    windowing (:264-660).  Six empty stub modules make the import succeed; callers that need
+    ``get_corner_lonlats`` patch the single astropy call with a stated closed form (tests/golden/make_golden_satcam.py).
+    Returns (SatCam module, orbit_gen module, sim dir)."""
+    if not os.path.isdir(os.path.join(REF_ROOT, "sim")):
+        raise RuntimeError("reference not present at %s" % REF_ROOT)
+    _stub_modules()
+    def stub(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None:
+            try:
+                __import__(name)
+                return sys.modules[name]
+            except Exception:
+                m = types.ModuleType(name)
+                sys.modules[name] = m
+        for k, v in attrs.items():
+            if not hasattr(m, k):
+                setattr(m, k, v)
+        return m
+
+    class EarthLocation:                      # placeholder; patched by the caller where needed
+        @staticmethod
+        def from_geocentric(*a, **k):
+            raise NotImplementedError("astropy is not installed; patch get_corner_lonlats")
+
+    astropy = stub("astropy")
+    astropy.coordinates = stub("astropy.coordinates", EarthLocation=EarthLocation)
+    rasterio = stub("rasterio")
+    rasterio.merge = stub("rasterio.merge", merge=None)
+    rasterio.windows = stub("rasterio.windows", from_bounds=None, transform=None)
+    stub("pyproj")
+    sim = os.path.join(REF_ROOT, "sim")
+    if sim not in sys.path:
+        sys.path.insert(0, sim)
+    import SatCam as SatCamMod
+    import orbit_gen
+    return SatCamMod, orbit_gen, sim

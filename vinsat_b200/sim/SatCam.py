@@ -19,6 +19,8 @@ _DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 A_M = 6378137.0
 C_M = 6356752.314245
 _E2 = 1.0 - (C_M * C_M) / (A_M * A_M)
+DEFAULT_REGIONS = ['10S', '10T', '11R', '12R', '16T', '17R', '17T', '18S',                 # SatCam.py:64-65
+                   '32S', '32T', '33S', '33T', '52S', '53S', '54S', '54T']
 
 
 def load_landmarks(regions=None):
@@ -76,8 +78,7 @@ class SatCam:
         self.f = (w_px / 2) / np.tan(half_angle)
         self.vfov = np.rad2deg(2 * np.arctan((h_px / 2) / self.f))
         self.K = np.array([[self.f, 0, w_px / 2], [0, self.f, h_px / 2], [0, 0, 1]])
-        self.regions = regions if regions is not None else ['10S', '10T', '11R', '12R', '16T', '17R', '17T', '18S',
-                                                            '32S', '32T', '33S', '33T', '52S', '53S', '54S', '54T']
+        self.regions = regions if regions is not None else list(DEFAULT_REGIONS)
         self.grid = getMGRS()
         self._ctx = _lib.default_context(config.device)
         self._landmarks = load_landmarks()
