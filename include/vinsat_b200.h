@@ -209,6 +209,34 @@ int vinsat_satcam_project(vinsat_ctx* ctx, int mem, int64_t n_poses, int64_t n_l
  * (tl,tr,br,bl), hit_out [P,4] uint8. */
 int vinsat_satcam_corners(vinsat_ctx* ctx, int mem, int64_t n_poses, const double* poses, double hfov_deg,
                           int32_t w_px, int32_t h_px, double* corners_out, uint8_t* hit_out);
+/* Same, plus the unit corner rays of get_corner_vectors (SatCam.py:94-104): vec_out [P,4,3] nullable. */
+int vinsat_satcam_corner_rays(vinsat_ctx* ctx, int mem, int64_t n_poses, const double* poses, double hfov_deg,
+                              int32_t w_px, int32_t h_px, double* corners_out, uint8_t* hit_out, double* vec_out);
+/* world_to_pixel_mat (SatCam.py:87-92) for every pose: C_out [P,3,4]. */
+int vinsat_satcam_cam_matrix(vinsat_ctx* ctx, int mem, int64_t n_poses, const double* poses, double hfov_deg,
+                             int32_t w_px, int32_t h_px, double* C_out);
+
+/* ---- a10: the reference's visibility predicate, batched (sim/SatCam.py:175-262 driven per pose by
+ *          sim/nadir_sim.py:175,198) ------------------------------------------------------------------------
+ * Landmark table, resident on the device: region r (code = zone*32 + letter, 'A'=1; '10S' = 10*32+19) owns rows
+ * region_off[r] .. region_off[r+1] of centroid_lonlat [n,2] (the 'Centroid Longitude', 'Centroid Latitude' columns of
+ * sim/landmark_csvs/<region>_top_salient.csv in row order; host pointers).  active_codes = `self.regions`
+ * (SatCam.py:63-67): only those regions are ever tested (:258). */
+typedef struct vinsat_satcam_table vinsat_satcam_table;
+int vinsat_satcam_table_create(vinsat_ctx* ctx, int32_t n_regions, const int32_t* region_codes,
+                               const int64_t* region_off, const double* centroid_lonlat, int32_t n_active,
+                               const int32_t* active_codes, vinsat_satcam_table** out);
+int vinsat_satcam_table_destroy(vinsat_satcam_table* table);
+/* check_for_all_landmarks (SatCam.py:254-262) for every pose: corner rays -> WGS84 ellipsoid (cast_ray_to_earth,
+ * :125-147) -> geodetic lon/lat (get_corner_lonlats, :175-185; astropy's conversion is replaced by the closed form for
+ * a point on the ellipsoid) -> get_region (:187-191) -> find_current_regions (:203-230) ->
+ * check_for_landmarks_in_region (:232-251; the best_classes blob is not shipped: all classes).
+ * visible_out [P] uint8 = what the reference returns.  Nullable extras: count_out [P] = landmarks counted without
+ * the early exits; corner_lonlat_out [P,4,2] (NaN where the ray misses); corner_region_out [P,4] region codes (-1 = None).
+ * With VINSAT_MEM_DEVICE the call is asynchronous on the context stream. */
+int vinsat_satcam_visibility(vinsat_ctx* ctx, const vinsat_satcam_table* table, int mem, int64_t n_poses,
+                             const double* poses, double hfov_deg, int32_t w_px, int32_t h_px, uint8_t* visible_out,
+                             int32_t* count_out, double* corner_lonlat_out, int32_t* corner_region_out);
 
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* FP64 FMA peak of the device (DFMA microbenchmark), TFLOP/s; and a device copy bandwidth, GB/s. */

@@ -109,6 +109,37 @@ def golden_ba():
         print(name, "saved; final |pos-gt|max = %.3f km; lamdas" % err, lams)
 
 
+def golden_ba_large():
+    """T=200, K=10 (the no-pivot block LU is most exposed at T >= 200 in the full phase, cond 1e11-5e12).
+    Histories only (the dense Jf / Hq blocks are pinned by the small cases).  ~2 min of reference time."""
+    pr = synth.make_problem(17, 200, 10)
+    hist, lams, hess = run_ref_ba(pr)
+    out = {("in_" + k): v for k, v in pr.items()}
+    out.update(states_hist=hist, lamda_hist=lams, hessian_hist=hess)
+    np.savez_compressed(os.path.join(HERE, "ba_T200.npz"), **out)
+    print("ba_T200 saved; final |pos-gt|max = %.3f km; lamdas" % np.abs(hist[-1][:, :3] - pr["states_gt"][:, :3]).max(), lams)
+
+
+def golden_ba_skip():
+    """20 BA iterations through `predict_gpu` (BA_filtering.py:16-17), i.e. with propagate_orbit_dynamics_skip
+    (steps of up to 100 s).  The reference takes this branch when torch.cuda.is_available(); there is no GPU in the
+    build container, so availability is forced and `Tensor.cuda()` is made the identity -- the arithmetic is the same
+    ATen code on the CPU device.  Gaps up to 250 s so that several 100 s hops and zero-length last hops occur."""
+    pr = synth.make_problem(23, 36, 6, gap_max=250)
+    avail, cuda = torch.cuda.is_available, torch.Tensor.cuda
+    torch.cuda.is_available = lambda: True
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        hist, lams, hess = run_ref_ba(pr)
+    finally:
+        torch.cuda.is_available, torch.Tensor.cuda = avail, cuda
+    out = {("in_" + k): v for k, v in pr.items()}
+    out.update(states_hist=hist, lamda_hist=lams, hessian_hist=hess)
+    np.savez_compressed(os.path.join(HERE, "ba_T36_skip100.npz"), **out)
+    print("ba_T36_skip100 saved; gaps max", int(np.diff(pr["time_idx"]).max()), "final |pos-gt|max = %.3f km; lamdas"
+          % np.abs(hist[-1][:, :3] - pr["states_gt"][:, :3]).max(), lams)
+
+
 def golden_long_gap():
     """Gaps > 100 s so that skip mode takes several 100 s hops and a zero-length last hop."""
     rng = np.random.default_rng(5)
@@ -191,14 +222,36 @@ def make_mgrs_table():
         json.dump([[k] + [int(x) for x in v] for k, v in table.items()], f, separators=(",", ":"))
 
 
+def make_batch_runner_commands():
+    """eval/batch_runner.py is a module-level loop of subprocess.call()s: run it with the call recorded, not executed."""
+    import json
+    import runpy
+    import subprocess
+    calls = []
+    real = subprocess.call
+    subprocess.call = lambda cmd, **kw: calls.append([cmd, kw]) or 0
+    try:
+        runpy.run_path("/root/reference/eval/batch_runner.py", run_name="__main__")
+    finally:
+        subprocess.call = real
+    with open(os.path.join(HERE, "batch_runner_commands.json"), "w") as f:
+        json.dump(calls, f, indent=0)
+    print("batch_runner_commands saved:", len(calls), "calls")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("ba", "all"):
         golden_ba()
         golden_long_gap()
+    if what in ("ba_large", "all"):
+        golden_ba_large()
+    if what in ("ba_skip", "all"):
+        golden_ba_skip()
     if what in ("helpers", "all"):
         golden_helpers()
         make_mgrs_table()
+        make_batch_runner_commands()
     if what in ("indexing", "streaming", "all"):
         import make_golden_streaming  # noqa: F401  (kept separate: slower)
         make_golden_streaming.main(what)

@@ -116,7 +116,8 @@ def _run_batch_vs_golden(ctx, names, mode=_lib.MODE_STEP1S):
             # oracle step from the ORACLE's own iterate (tracks the reference to < 1e-4 m)
             st_or[p], lam_or[p], Ho, info = o.ba_iteration(it, st_or[p], pr["cum_rot"], pr["uv"], pr["xyz"], pr["ii"],
                                                            pr["time_idx"], pr["intr"], pr["conf"], lam_or[p],
-                                                           initialize=init)
+                                                           initialize=init,
+                                                           mode="skip100" if mode == _lib.MODE_SKIP100 else "step1s")
             ref = g["states_hist"][it]
             s = st[f0:f1]
             assert np.abs(s[:, :3] - ref[:, :3]).max() < 1e-3, (names[p], it)        # 1 m
@@ -152,6 +153,26 @@ def test_ba_two_sided_fused_sweep_tracks_reference(ctx, monkeypatch):
     segment per problem.  States / lamda schedule / trial counts / last Hessian against the REFERENCE's history."""
     monkeypatch.setenv("VINSAT_SEG_LEN", "1000000")
     _run_batch_vs_golden(ctx, BA_CASES)
+
+
+def test_ba_skip100_mode_tracks_reference_predict_gpu(ctx):
+    """20 iterations with the 100 s-step propagator against the reference's `predict_gpu` branch
+    (tests/golden/make_golden.py::golden_ba_skip; gaps up to 250 s)."""
+    _run_batch_vs_golden(ctx, ["ba_T36_skip100"], mode=_lib.MODE_SKIP100)
+
+
+@pytest.mark.parametrize("path", ["default", "two_sided_fused", "one_sided", "materialised", "partitioned_13"])
+def test_ba_T200_tracks_reference_on_every_solver_path(ctx, monkeypatch, path):
+    """T=200, K=10 reference history (the no-pivot block LU at cond 1e11..5e12) through every solver
+    path: the default for this batch size, the Monte-Carlo path (two chains per problem, fused system build), one
+    chain per problem, materialised [D|U|b] records, and the partitioned sweep with 13-frame segments."""
+    env = {"default": {}, "two_sided_fused": {"VINSAT_SEG_LEN": "1000000"},
+           "one_sided": {"VINSAT_SEG_LEN": "1000000", "VINSAT_ONE_SIDED_SWEEP": "1"},
+           "materialised": {"VINSAT_SEG_LEN": "1000000", "VINSAT_NO_FUSED_SYSTEM": "1"},
+           "partitioned_13": {"VINSAT_SEG_LEN": "13"}}[path]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _run_batch_vs_golden(ctx, ["ba_T200"])
 
 
 def test_system_blocks_exact_inputs(ctx):
@@ -307,7 +328,7 @@ def _nadir_poses(n, seed):
     return np.concatenate([pos, d, up, r], axis=1)
 
 
-def test_satcam_projection_and_visibility_bit_exact(ctx):
+def test_satcam_projection_and_inframe_mask_bit_exact(ctx):
     poses = _nadir_poses(70, 0)
     rng = np.random.default_rng(1)
     lon = rng.uniform(-180, 180, 500); lat = rng.uniform(-80, 80, 500)
@@ -317,14 +338,15 @@ def test_satcam_projection_and_visibility_bit_exact(ctx):
     lm = np.concatenate([lm, sub + rng.normal(0, 50e3, size=sub.shape)])
     uv, mask, cnt = ctx.satcam_project(poses, lm, 66.0, 4608, 2592)
     uvo, masko = so.project(poses, lm, 66.0, 4608, 2592)
-    assert np.array_equal(mask.astype(bool), masko), "visibility sets must be bit-exact"
+    assert np.array_equal(mask.astype(bool), masko), "in-frame sets must be bit-exact"
     assert masko.sum() > 20
     assert np.array_equal(uv[masko], uvo[masko])
     assert np.array_equal(cnt, masko.sum(axis=1))
     corners, hit = ctx.satcam_corners(poses, 66.0, 4608, 2592)
     co, ho = so.corners(poses, 66.0, 4608, 2592)
     assert np.array_equal(hit.astype(bool), ho) and ho.all()
-    assert np.array_equal(corners, co)
+    # the oracle squares with libm pow() like the reference (rarely one ulp off x*x); see tests/test_gpu_satcam.py
+    assert (corners != co).mean() < 2e-3 and np.abs(corners - co).max() <= 4e-9
     # a camera looking away from the Earth misses it
     away = poses.copy(); away[:, 3:6] *= -1
     _, hit2 = ctx.satcam_corners(away, 66.0, 4608, 2592)

@@ -101,3 +101,16 @@ def test_mgrs_table_equals_reference_order_and_values():
     got = [[k] + [int(x) for x in v] for k, v in getMGRS().items()]
     assert got == ref and len(got) == 1197
 
+
+
+def test_batch_runner_main_issues_the_reference_commands():
+    """`python batch_runner.py` of the reference = 32 subprocess.call()s (recorded by tests/golden/make_golden.py
+    with the call patched out); the mirror's main() must issue exactly those."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from vinsat_b200.eval import batch_runner
+    want = json.load(open(os.path.join(GOLDEN, "batch_runner_commands.json")))
+    got = []
+    batch_runner.main(call=lambda cmd, **kw: got.append([cmd, kw]) or 0)
+    assert got == want and len(got) == 32

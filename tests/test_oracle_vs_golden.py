@@ -79,6 +79,22 @@ def test_ba_iterates_track_reference(name, dense):
         assert rel(H, g["hessian_hist"][it]) < 1e-6, it
 
 
+@pytest.mark.parametrize("name,mode", [("ba_T36_skip100", "skip100"), ("ba_T200", "step1s")])
+def test_ba_iterates_track_reference_skip_mode_and_T200(name, mode):
+    """The `predict_gpu` branch (100 s steps, gaps up to 250 s) and a T=200 arc: same bar as above."""
+    g = load_golden(name); pr = problem_from_golden(g)
+    st, lam = pr["states0"].copy(), 1e-4
+    for it in range(20):
+        st, lam, H, info = o.ba_iteration(it, st, pr["cum_rot"], pr["uv"], pr["xyz"], pr["ii"], pr["time_idx"],
+                                          pr["intr"], pr["conf"], lam, initialize=(it < 10), mode=mode)
+        ref = g["states_hist"][it]
+        assert np.abs(st[:, :3] - ref[:, :3]).max() < 1e-3, it
+        assert np.abs(st[:, 7:] - ref[:, 7:]).max() < 1e-6, it
+        assert np.abs(st[:, 3:7] - ref[:, 3:7]).max() < 1e-7, it
+        assert lam == g["lamda_hist"][it], it
+        assert rel(H, g["hessian_hist"][it]) < 1e-6, it
+
+
 def test_helpers():
     g = load_golden("helpers")
     assert rel(o.quat_mul(g["q1"], g["q2"]), g["qmul"]) < 1e-15

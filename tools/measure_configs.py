@@ -46,10 +46,13 @@ elif what == "c5":
     north = np.cross(up, east)
     poses = np.concatenate([pos, -up, north, east], axis=1)
     out["note"] = "poses from %d seeded 3 h polar arcs at 1 Hz, nadir pointing" % n_arc
-    SC.visibility_sweep(poses[:8192], L, chunk=8192)
-    t0 = time.time(); counts = SC.visibility_sweep(poses, L, chunk=8192); dt = time.time() - t0
+    SC.inframe_sweep(poses[:8192], L, chunk=8192)
+    t0 = time.time(); counts = SC.inframe_sweep(poses, L, chunk=8192); dt = time.time() - t0
     out.update(n_poses=len(poses), n_landmarks=len(L), sweep_s=dt, poses_per_s=len(poses) / dt, pairs_per_s=len(poses) * len(L) / dt,
-               mean_visible=float(counts.mean()), max_visible=int(counts.max()))
+               mean_inframe=float(counts.mean()), max_inframe=int(counts.max()))
+    SC.visibility_sweep(poses[:8192])
+    t0 = time.time(); vis = SC.visibility_sweep(poses); dt = time.time() - t0
+    out.update(visibility_s=dt, visibility_poses_per_s=len(poses) / dt, n_visible=int(vis.sum()))
 elif what == "c3":
     T = int(sys.argv[2]) if len(sys.argv) > 2 else 100_000
     t0 = time.time(); pr = synth.make_problem(5, T, 50, gap_max=3); out["synth_s"] = time.time() - t0

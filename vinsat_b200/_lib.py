@@ -81,6 +81,15 @@ SIGNATURES = {
                                         C.c_double, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vinsat_satcam_corners": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_int32,
                                         C.c_int32, C.c_void_p, C.c_void_p]),
+    "vinsat_satcam_corner_rays": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_int32,
+                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_satcam_cam_matrix": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double, C.c_int32,
+                                           C.c_int32, C.c_void_p]),
+    "vinsat_satcam_table_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                             C.c_void_p, C.POINTER(C.c_void_p)]),
+    "vinsat_satcam_table_destroy": (C.c_int, [C.c_void_p]),
+    "vinsat_satcam_visibility": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double,
+                                           C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vinsat_measure_fp64_peak": (C.c_int, [C.c_void_p, c_dp]),
     "vinsat_measure_copy_bw": (C.c_int, [C.c_void_p, C.c_int64, c_dp]),
 }
@@ -272,14 +281,68 @@ class Context:
                                                   int(w_px), int(h_px), _ptr(uv), _ptr(mask), _ptr(cnt)))
         return uv, mask, cnt
 
-    def satcam_corners(self, poses, hfov, w_px, h_px):
+    def satcam_corners(self, poses, hfov, w_px, h_px, want_rays=False):
         poses = f64(poses).reshape(-1, 12)
         P = poses.shape[0]
         corners = np.empty((P, 4, 3))
         hit = np.empty((P, 4), dtype=np.uint8)
-        self.check(self.lib.vinsat_satcam_corners(self.h, MEM_HOST, P, _ptr(poses), float(hfov), int(w_px),
-                                                  int(h_px), _ptr(corners), _ptr(hit)))
-        return corners, hit
+        vec = np.empty((P, 4, 3)) if want_rays else None
+        self.check(self.lib.vinsat_satcam_corner_rays(self.h, MEM_HOST, P, _ptr(poses), float(hfov), int(w_px),
+                                                      int(h_px), _ptr(corners), _ptr(hit), _ptr(vec)))
+        return (corners, hit, vec) if want_rays else (corners, hit)
+
+    def satcam_cam_matrix(self, poses, hfov, w_px, h_px):
+        poses = f64(poses).reshape(-1, 12)
+        Cm = np.empty((poses.shape[0], 3, 4))
+        self.check(self.lib.vinsat_satcam_cam_matrix(self.h, MEM_HOST, poses.shape[0], _ptr(poses), float(hfov),
+                                                     int(w_px), int(h_px), _ptr(Cm)))
+        return Cm
+
+    def satcam_table(self, region_codes, region_off, centroid_lonlat, active_codes):
+        """Device-resident landmark table for `satcam_visibility` (see include/vinsat_b200.h)."""
+        return SatcamTable(self, region_codes, region_off, centroid_lonlat, active_codes)
+
+    def satcam_visibility(self, table, poses, hfov, w_px, h_px, want_count=False, want_corners=False):
+        """check_for_all_landmarks for every pose -> visible (P,) bool [, count (P,), corner lon/lat (P,4,2),
+        corner region codes (P,4)]."""
+        poses = f64(poses).reshape(-1, 12)
+        P = poses.shape[0]
+        vis = np.zeros(P, dtype=np.uint8)
+        cnt = np.zeros(P, dtype=np.int32) if want_count else None
+        ll = np.empty((P, 4, 2)) if want_corners else None
+        reg = np.empty((P, 4), dtype=np.int32) if want_corners else None
+        self.check(self.lib.vinsat_satcam_visibility(self.h, table.h, MEM_HOST, P, _ptr(poses), float(hfov),
+                                                     int(w_px), int(h_px), _ptr(vis), _ptr(cnt), _ptr(ll), _ptr(reg)))
+        out = [vis.astype(bool)]
+        if want_count:
+            out.append(cnt)
+        if want_corners:
+            out += [ll, reg]
+        return out[0] if len(out) == 1 else tuple(out)
+
+
+class SatcamTable:
+    def __init__(self, ctx, region_codes, region_off, centroid_lonlat, active_codes):
+        self.ctx = ctx
+        codes = np.ascontiguousarray(region_codes, dtype=np.int32)
+        off = i64(region_off)
+        ll = f64(centroid_lonlat).reshape(-1, 2)
+        act = np.ascontiguousarray(active_codes, dtype=np.int32)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.vinsat_satcam_table_create(ctx.h, len(codes), _ptr(codes), _ptr(off), _ptr(ll), len(act),
+                                                     _ptr(act), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.lib.vinsat_satcam_table_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def bind_host_thread_to_gpu(device):

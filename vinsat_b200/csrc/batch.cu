@@ -182,6 +182,7 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
     for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     b->graphs.clear();
     b->graph_warm.clear();
+    b->graph_bad.clear();
   }
   b->frame_off.assign(d->frame_off, d->frame_off + P + 1);
   b->obs_off.assign(d->obs_off, d->obs_off + P + 1);
@@ -361,8 +362,16 @@ static int wait_flag(vinsat_batch* b) {
   static const bool no_spin = getenv("VINSAT_NO_SPIN_WAIT") != nullptr;
   if (!no_spin) {
     volatile int32_t* f = b->h_flags;
-    for (int64_t spins = 0; spins < 400000000ll; spins++) {
+    for (int64_t spins = 0;; spins++) {
       if (f[0] != -1) return VINSAT_OK;
+      // every ~64k polls ask the driver: a finished stream (the copy has landed or will never land) or a faulted
+      // one ends the spin at once instead of burning a core until a timeout
+      if ((spins & 0xffff) == 0xffff) {
+        const cudaError_t q = cudaStreamQuery(ctx->stream);
+        if (q == cudaSuccess) return VINSAT_OK;
+        if (q != cudaErrorNotReady)
+          return set_error(ctx, VINSAT_ECUDA, "stream failed while waiting for an LM trial: %s", cudaGetErrorString(q));
+      }
 #if defined(__x86_64__) || defined(__i386__)
       __builtin_ia32_pause();
 #endif
@@ -446,21 +455,30 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
                          ((uint64_t)(b->st == b->st_base ? 1 : 0) << 21) | ((uint64_t)(b->r == b->r_base ? 1 : 0) << 22) |
                          ((uint64_t)(have_residuals ? 1 : 0) << 23) | ((uint64_t)(b->fused_system ? 1 : 0) << 24);
     auto it = b->graphs.find(key);
-    if (it == b->graphs.end() && b->graph_warm.count(key)) {
+    // the legacy / per-thread default streams cannot be captured: plain launches there
+    const bool capturable = ctx->stream != nullptr && ctx->stream != cudaStreamLegacy && ctx->stream != cudaStreamPerThread;
+    if (it == b->graphs.end() && b->graph_warm.count(key) && capturable && !b->graph_bad.count(key)) {
       cudaGraph_t g = nullptr;
       const int64_t l0 = ctx->launches;
-      VS_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = issue_iteration_head(b, iter, initialize, mode, lam_dev_in, have_residuals);
-      const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
-      if (rc != VINSAT_OK) { if (g) cudaGraphDestroy(g); return rc; }
-      VS_CUDA(ctx, ce);
-      vinsat_batch::IterGraph ig;
-      ig.n_launches = ctx->launches - l0;
-      ctx->launches = l0;
-      const cudaError_t ie = cudaGraphInstantiate(&ig.exec, g, 0);
-      cudaGraphDestroy(g);
-      VS_CUDA(ctx, ie);
-      it = b->graphs.emplace(key, ig).first;
+      if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int rc = issue_iteration_head(b, iter, initialize, mode, lam_dev_in, have_residuals);
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &g);
+        vinsat_batch::IterGraph ig;
+        ig.n_launches = ctx->launches - l0;       // launches recorded into the graph, counted again at every replay
+        ctx->launches = l0;
+        cudaError_t ie = cudaErrorUnknown;
+        if (rc == VINSAT_OK && ce == cudaSuccess && g) ie = cudaGraphInstantiate(&ig.exec, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (ie == cudaSuccess) {
+          it = b->graphs.emplace(key, ig).first;
+        } else {
+          cudaGetLastError();                 // capture / instantiate failed: clear it and never try this key again
+          b->graph_bad.insert(key);
+        }
+      } else {
+        cudaGetLastError();
+        b->graph_bad.insert(key);
+      }
     }
     if (it != b->graphs.end()) {
       VS_CUDA(ctx, cudaGraphLaunch(it->second.exec, ctx->stream));
@@ -490,6 +508,11 @@ int vinsat_batch_ba_iterate(vinsat_batch* b, int iter, int initialize, int mode,
   if (!b || !lamda_io) return set_error(b ? b->ctx : nullptr, VINSAT_EINVAL, "vinsat_batch_ba_iterate: NULL argument");
   vinsat_ctx* ctx = b->ctx;
   VS_CHECK_ARG(ctx, mode == VINSAT_MODE_STEP1S || mode == VINSAT_MODE_SKIP100);
+  // The LM loop multiplies lamda by 10 until lamda > 1e4 (BA_filtering.py:74-77); the device loop is bounded at 16
+  // trials, which covers every lamda >= 1e-10 (the reference itself never hands back less than 1e-4, :79).
+  for (int64_t p = 0; p < b->P; p++)
+    if (!(lamda_io[p] >= 1e-10 && lamda_io[p] <= 1e300))
+      return set_error(ctx, VINSAT_EINVAL, "lamda_io[%lld] = %g outside [1e-10, inf)", (long long)p, lamda_io[p]);
   VS_CUDA(ctx, cudaSetDevice(ctx->device));
   VS_CUDA(ctx, cudaMemcpyAsync(b->lam_next, lamda_io, b->P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   VS_TRY(ba_iterate_device(b, iter, initialize, mode, b->lam_next));
@@ -505,6 +528,7 @@ int vinsat_batch_od_solve(vinsat_batch* b, int num_iters, int n_init, double lam
   vinsat_ctx* ctx = b->ctx;
   VS_CHECK_ARG(ctx, mode == VINSAT_MODE_STEP1S || mode == VINSAT_MODE_SKIP100);
   VS_CHECK_ARG(ctx, num_iters >= 0);
+  VS_CHECK_ARG(ctx, lamda_init >= 1e-10 && lamda_init <= 1e300);     // see vinsat_batch_ba_iterate
   VS_CUDA(ctx, cudaSetDevice(ctx->device));
   double* h = (double*)ctx_pinned(ctx, b->P * sizeof(double));
   if (!h) return set_error(ctx, VINSAT_ENOMEM, "pinned scratch failed");

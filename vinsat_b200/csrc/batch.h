@@ -61,6 +61,7 @@ struct vinsat_batch {
   // launches depend on (iteration index, phase, propagator, which of the ping-pong buffers is current)
   struct IterGraph { cudaGraphExec_t exec = nullptr; int64_t n_launches = 0; };
   std::map<uint64_t, IterGraph> graphs;
+  std::set<uint64_t> graph_bad;       // keys whose capture / instantiation failed: plain launches from then on
   std::set<uint64_t> graph_warm;      // keys that ran eagerly once (function attributes set, scratch grown)
   const double* st_base = nullptr;    // identity of the ping-pong buffers at creation
   const double* r_base = nullptr;

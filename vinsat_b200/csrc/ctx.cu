@@ -169,6 +169,7 @@ int vinsat_ctx_create(int device, vinsat_ctx** out) {
   cudaDeviceProp prop;
   VS_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   VS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   *out = ctx;

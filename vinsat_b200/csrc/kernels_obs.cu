@@ -99,7 +99,10 @@ __global__ void __launch_bounds__(256) k_obs_index(int64_t M, int64_t T, int P, 
   int64_t prev = -1;
   if (k > 0) {
     const int pp = find_problem(obs_off, P, k - 1);
-    prev = frame_off[pp] + ii_local[k - 1];
+    const int64_t ilp = ii_local[k - 1];
+    // an out-of-range predecessor is flagged by its own thread; never derive a fill range from it
+    if (ilp < 0 || ilp >= frame_off[pp + 1] - frame_off[pp]) return;
+    prev = frame_off[pp] + ilp;
   }
   if (f < prev) { atomicOr(&flags[1], 2); return; }    // not sorted by frame
   for (int64_t j = prev + 1; j <= f; j++) obs_start[j] = (int32_t)k;
@@ -625,22 +628,14 @@ int launch_obs_assemble(vinsat_batch* b, double alpha) {
   if (b->T == 0) return VINSAT_OK;
   static int variant = getenv("VINSAT_ASM_VARIANT") ? atoi(getenv("VINSAT_ASM_VARIANT")) : 0;
   if (variant == 32) {            // thread-per-frame walk (kept for comparison)
-    static bool attr_set = false;
     const int smem = 6 * 352 * (int)sizeof(double);
-    if (!attr_set) {
-      VS_CUDA(ctx, cudaFuncSetAttribute(k_obs_assemble_staged<32, 352, 1, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
+    VS_SMEM_OPTIN(ctx, SM_ASM_STAGED, (k_obs_assemble_staged<32, 352, 1, 12>), smem);
     VS_LAUNCH(ctx, F_OBS_ASSEMBLE, (k_obs_assemble_staged<32, 352, 1, 12>), ceil_div(b->T, 32), 32, smem, b->T, b->M,
               b->obs_start, b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
     return VINSAT_OK;
   }
-  static bool attr_set = false;
   const int smem = (k2pSlots * k2pChunk + 32 * k2pFrameRec) * (int)sizeof(double) + k2pChunk * (int)sizeof(int32_t);
-  if (!attr_set) {
-    VS_CUDA(ctx, cudaFuncSetAttribute(k_obs_assemble_2pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  VS_SMEM_OPTIN(ctx, SM_ASM_2PASS, k_obs_assemble_2pass, smem);
   VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_2pass, ceil_div(b->T, 32), 32, smem, b->T, b->M, b->obs_start, b->oframe,
             b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax, b->gate_arg);
   return VINSAT_OK;

@@ -252,11 +252,7 @@ int launch_select_median(vinsat_batch* b) {
   if (!no_smem && keys > 0 && keys <= 24000 && !b->window) {
     vinsat_ctx* ctx = b->ctx;
     const int smem = (int)((keys + kSelCand) * sizeof(unsigned long long));
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-      VS_CUDA(ctx, cudaFuncSetAttribute(k_select_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_smem = smem;
-    }
+    VS_SMEM_OPTIN(ctx, SM_SELECT, k_select_smem, smem);
     VS_LAUNCH(ctx, F_SELECT, k_select_smem, (unsigned)b->P, kSelThreads, smem, b->M, b->d_obs_off, b->r, b->c_obs,
               b->gate_arg);
     return VINSAT_OK;
@@ -400,11 +396,7 @@ int launch_system_build(vinsat_batch* b, int initialize, double Sigma, double ve
   vinsat_ctx* ctx = b->ctx;
   if (b->T == 0) return VINSAT_OK;
   const int smem = kSysFrames * (kSysStride + kSysOut) * (int)sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    VS_CUDA(ctx, cudaFuncSetAttribute(k_system_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  VS_SMEM_OPTIN(ctx, SM_SYSROWS, k_system_rows, smem);
   VS_LAUNCH(ctx, F_SYSTEM, k_system_rows, ceil_div(b->T, kSysFrames), 96, smem, b->T, b->gap, b->fprob, b->wmax,
             b->grec, b->drec, initialize, Sigma, vel_coeff, b->srec);
   return VINSAT_OK;

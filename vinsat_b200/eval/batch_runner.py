@@ -1,22 +1,34 @@
 """``eval/batch_runner.py`` of the reference is an 11-line script that loops over 16 MGRS regions and runs
-``eval_landmarks.py`` (YOLO detector evaluation) in subprocesses; it has no callable API and no
-estimation code.  `main()` keeps exactly that behaviour.  The Monte-Carlo OD runner BASELINE.json's configs name
-is ADDED here as `run_od_monte_carlo` without changing what `python batch_runner.py` does.
+``eval_landmarks.py`` (YOLO detector evaluation) twice per region in subprocesses; it has no callable
+API and no estimation code.  `main()` issues exactly the reference's two command strings per region
+(eval/batch_runner.py:7-11).  The Monte-Carlo OD runner BASELINE.json's configs name is ADDED here as
+`run_od_monte_carlo` / `run_od_pool` without changing what `python batch_runner.py` does.
 """
-import os
 import subprocess
 
 import numpy as np
 
-REGIONS = ['10S', '10T', '11R', '12R', '16T', '17R', '17T', '18S', '32S', '32T', '33S', '33T', '52S', '53S', '54S', '54T']
+regions = ['10S', '10T', '11R', '12R', '16T', '17R', '17T', '18S',                      # eval/batch_runner.py:3-5
+           '32S', '32T', '33S', '33T', '52S', '53S', '54S', '54T']
+REGIONS = regions
 
 
-def main():
-    """eval/batch_runner.py:1-11: two eval_landmarks.py runs per region."""
-    for key in REGIONS:
-        print("\nKEY: ", key)
-        subprocess.call(f'python eval_landmarks.py -m ../sim/models/{key}_n100.pt -v ../../{key}_n100/val -t 3 -b ../sim/best_classes/{key}_best_classes.npy -c ../sim/best_confs/{key}_best_confs.npy --px 5 -o 10 --calculate_err', shell=True)
-        subprocess.call(f'python eval_landmarks.py -m ../sim/models/{key}_n100.pt -v ../../{key}_n100/val -t 3 -b ../sim/best_classes/{key}_best_classes.npy -c ../sim/best_confs/{key}_best_confs.npy --px 5 -o 10', shell=True)
+def region_commands(region):
+    """The two shell commands of eval/batch_runner.py:8 and :10 for one region (detector error evaluation, then the
+    best-class / best-confidence search)."""
+    return ("python eval_landmarks.py --model_path ../sim/models/" + region + ".pt --im_path datasets/" + region
+            + "/images --lab_path datasets/" + region + "/labels --output_path " + region
+            + "_err.npy --calculate_err --save_err",
+            "python eval_landmarks.py --err_path " + region + "_err.npy --best_classes --save_best_conf"
+            " --best_classes_path ../sim/best_classes/" + region + "_best_classes.npy --best_conf_path ../sim/best_confs/"
+            + region + "_best_conf.npy --px_threshold 10")
+
+
+def main(call=subprocess.call):
+    """eval/batch_runner.py:7-11."""
+    for region in regions:
+        for command in region_commands(region):
+            call(command, shell=True)
 
 
 def run_od_monte_carlo(n_problems, frames=1000, obs_per_frame=10, seed0=0, sigma_px=1.0, device=None, rank=0,

@@ -1,7 +1,8 @@
 """Mirror of ``sim/SatCam.py`` (live part, :15-262): pinhole camera in ECEF, world->pixel matrix, corner
 ray-cast to the WGS84 ellipsoid, MGRS region lookup, landmark-in-footprint test -- plus the batched entry
 points the trajectory-generation sweep needs (config 5 of BASELINE.json).  Geometry runs on the device
-(``vinsat_satcam_project`` / ``vinsat_satcam_corners``).
+(``vinsat_satcam_project`` / ``vinsat_satcam_corner_rays`` / ``vinsat_satcam_visibility``), in the reference's own
+rounding order (pinned bit for bit by ``tests/golden/satcam.npz``, generated from the reference class).
 
 Third-party boundaries of the reference that are NOT available here (astropy geocentric->geodetic,
 SatCam.py:181; pyproj geodetic->geocentric, :194-199) are replaced by WGS84 closed forms; parity there is
@@ -71,6 +72,32 @@ class SatellitePose:                                            # SatCam.py:23-3
     def get_right_vec(self): return self.right_vec.get()
 
 
+def region_code(name):
+    """'10S' -> 10*32 + 19 (letter code 'A'=1): the integer form the C ABI uses for MGRS cells; None -> -1."""
+    return -1 if name is None else int(name[:2]) * 32 + (ord(name[2]) - 64)
+
+
+def region_name(code):
+    return None if code < 0 else "%02d%s" % (code // 32, chr(64 + code % 32))
+
+
+_TABLES = {}
+
+
+def landmark_table(ctx, regions=None):
+    """Device-resident landmark table (all shipped CSVs) with `regions` as the active set (SatCam.py:63-67);
+    cached per (context, active set)."""
+    active = tuple(DEFAULT_REGIONS if regions is None else regions)
+    key = (id(ctx), active)
+    if key not in _TABLES:
+        lm = load_landmarks()
+        names = sorted(lm)
+        off = np.cumsum([0] + [len(lm[n]) for n in names])
+        rows = np.concatenate([lm[n][:, :2] for n in names])
+        _TABLES[key] = ctx.satcam_table([region_code(n) for n in names], off, rows, [region_code(n) for n in active])
+    return _TABLES[key]
+
+
 class SatCam:
     def __init__(self, sat_pose, hfov, w_px, h_px, regions=None):          # SatCam.py:39-75
         self.hfov, self.w_px, self.h_px = hfov, w_px, h_px
@@ -81,7 +108,7 @@ class SatCam:
         self.regions = regions if regions is not None else list(DEFAULT_REGIONS)
         self.grid = getMGRS()
         self._ctx = _lib.default_context(config.device)
-        self._landmarks = load_landmarks()
+        self._table = landmark_table(self._ctx, self.regions)
         self.update_pose(sat_pose)
 
     def update_pose(self, sat_pose):                                        # SatCam.py:77-85
@@ -97,9 +124,11 @@ class SatCam:
         self.C_cw = self.world_to_pixel_mat()
 
     def world_to_pixel_mat(self):                                           # SatCam.py:87-92
-        t = self.R_cw @ self.sat_pos
-        E = np.concatenate((self.R_cw, -t[:, np.newaxis]), axis=1)
-        return self.K @ E
+        return self._ctx.satcam_cam_matrix(self._pose12[None], self.hfov, self.w_px, self.h_px)[0]
+
+    def get_corner_vectors(self):                                           # SatCam.py:98-104
+        _, _, vec = self._ctx.satcam_corners(self._pose12[None], self.hfov, self.w_px, self.h_px, want_rays=True)
+        return {k: vec[0, i] for i, k in enumerate(('tl', 'tr', 'br', 'bl'))}
 
     def ecef_pos_to_px(self, pos):                                          # SatCam.py:149-154
         pos = np.asarray(pos, dtype=np.float64)
@@ -112,16 +141,15 @@ class SatCam:
     def lonlat_to_pixel_coords(self, lon, lat):                             # SatCam.py:193-201
         return self.ecef_pos_to_px(lonlat_to_ecef(np.asarray(lon, dtype=np.float64), np.asarray(lat, dtype=np.float64)).T)
 
+    def _visibility(self):
+        vis, cnt, ll, reg = self._ctx.satcam_visibility(self._table, self._pose12[None], self.hfov, self.w_px,
+                                                        self.h_px, want_count=True, want_corners=True)
+        return bool(vis[0]), int(cnt[0]), ll[0], reg[0]
+
     def get_corner_lonlats(self):                                           # SatCam.py:175-185
-        corners, hit = self._ctx.satcam_corners(self._pose12[None], self.hfov, self.w_px, self.h_px)
-        out = {}
-        for k, key in enumerate(('tl', 'tr', 'br', 'bl')):
-            if hit[0, k]:
-                lon, lat = ecef_to_lonlat(corners[0, k])
-                out[key] = (float(lon), float(lat))
-            else:
-                out[key] = None
-        return out
+        _, _, ll, _ = self._visibility()
+        return {key: (None if np.isnan(ll[k, 0]) else (float(ll[k, 0]), float(ll[k, 1])))
+                for k, key in enumerate(('tl', 'tr', 'br', 'bl'))}
 
     def get_region(self, lon, lat):                                         # SatCam.py:187-191
         for key, bounds in self.grid.items():
@@ -130,42 +158,41 @@ class SatCam:
         return None
 
     def find_current_regions(self):                                         # SatCam.py:203-230
-        self.corner_lonlats = corner_lonlats = self.get_corner_lonlats()
-        regions = [self.get_region(*ll) for ll in corner_lonlats.values() if ll is not None]
-        num_bounds = [int(r[:2]) for r in regions if r is not None]
-        char_bounds = [r[2] for r in regions if r is not None]
-        if regions and regions[-1] is not None:       # the reference tests the loop variable of its last iteration
-            if min(num_bounds) < 4 and max(num_bounds) > 57:
-                num_range = [58, 59, 60, 1, 2, 3]
-            else:
-                num_range = range(min(num_bounds), max(num_bounds) + 1)
-            char_range = [chr(i) for i in range(ord(min(char_bounds)), ord(max(char_bounds)) + 1)]
-            self.current_regions = [str(n).zfill(2) + c for n in num_range for c in char_range]
+        _, _, ll, reg = self._visibility()
+        self.corner_lonlats = {key: (None if np.isnan(ll[k, 0]) else (float(ll[k, 0]), float(ll[k, 1])))
+                               for k, key in enumerate(('tl', 'tr', 'br', 'bl'))}
+        regions = [region_name(int(reg[k])) for k in range(4) if not np.isnan(ll[k, 0])]
+        if not regions:
+            raise UnboundLocalError("no image corner intersects the Earth (the reference fails here too, SatCam.py:217)")
+        nums = [int(r[:2]) for r in regions if r is not None]
+        chars = [r[2] for r in regions if r is not None]
+        if regions[-1] is not None:       # the reference tests the loop variable of its last iteration (:217)
+            num_range = [58, 59, 60, 1, 2, 3] if (min(nums) < 4 and max(nums) > 57) else range(min(nums), max(nums) + 1)
+            self.current_regions = [str(n).zfill(2) + chr(c) for n in num_range
+                                    for c in range(ord(min(chars)), ord(max(chars)) + 1)]
         else:
             self.current_regions = regions
         return self.current_regions
 
     def check_for_landmarks_in_region(self, region):                        # SatCam.py:232-251
+        """Count (capped at 3 by the reference's early return) of the region's centroids inside the tl/br box."""
         cl = self.corner_lonlats
-        if cl['tl'] is None or cl['br'] is None or region not in self._landmarks:
+        lm = load_landmarks().get(region)
+        if cl['tl'] is None or cl['br'] is None or lm is None:
             return 0
         tl_lon, tl_lat = cl['tl']
         br_lon, br_lat = cl['br']
-        lm = self._landmarks[region]
         inside = (lm[:, 0] > tl_lon) & (lm[:, 0] < br_lon) & (lm[:, 1] > br_lat) & (lm[:, 1] < tl_lat)
-        return int(min(inside.sum(), 3))                                     # early exit at 3 (:249-250)
+        return int(min(inside.sum(), 3))
 
     def check_for_all_landmarks(self):                                      # SatCam.py:254-262
-        num = 0
-        for region in self.find_current_regions():
-            if region in self.regions:
-                num += self.check_for_landmarks_in_region(region)
-                if num >= 3:
-                    return True
-        return False
+        vis, _, ll, _ = self._visibility()
+        self.corner_lonlats = {key: (None if np.isnan(ll[k, 0]) else (float(ll[k, 0]), float(ll[k, 1])))
+                               for k, key in enumerate(('tl', 'tr', 'br', 'bl'))}
+        return vis
 
 
-# ---- batched sweep (config 5): all landmark centroids x many poses -----------------------------------------
+# ---- batched sweeps (config 5): many poses at once ------------------------------------------------------------
 def all_landmark_centroids_ecef(regions=None):
     lm = load_landmarks(regions)
     names = sorted(lm)
@@ -173,9 +200,26 @@ def all_landmark_centroids_ecef(regions=None):
     return lonlat_to_ecef(rows[:, 0], rows[:, 1]), rows, names
 
 
-def visibility_sweep(poses, landmarks_ecef, hfov=66.0, w_px=4608, h_px=2592, chunk=4096, want_mask=False):
-    """poses (P,12) x landmarks (L,3) -> per-pose count of landmarks inside the image (and optionally the
-    (P,L) uint8 mask), computed on the device in pose chunks."""
+def rank_slice(n, rank, world_size):
+    """Contiguous block of poses owned by `rank` (poses are independent: no collective)."""
+    return (n * rank) // world_size, (n * (rank + 1)) // world_size
+
+
+def visibility_sweep(poses, hfov=66.0, w_px=4608, h_px=2592, regions=None, rank=0, world_size=1, want_count=False,
+                     device=None):
+    """The reference's per-pose predicate `SatCam.check_for_all_landmarks()` (sim/nadir_sim.py:175,198) for all
+    poses in ONE device call: poses (P,12) -> visible (P_rank,) bool [, landmark count].  With world_size > 1 the
+    rank evaluates its contiguous slice `rank_slice(P, rank, world_size)`; callers concatenate (or all-gather)."""
+    ctx = _lib.default_context(config.device if device is None else device)
+    poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 12)
+    lo, hi = rank_slice(poses.shape[0], rank, world_size)
+    return ctx.satcam_visibility(landmark_table(ctx, regions), poses[lo:hi], hfov, w_px, h_px, want_count=want_count)
+
+
+def inframe_sweep(poses, landmarks_ecef, hfov=66.0, w_px=4608, h_px=2592, chunk=4096, want_mask=False):
+    """poses (P,12) x landmarks (L,3) -> per-pose count of landmarks that project inside the image (and optionally
+    the (P,L) uint8 mask), computed on the device in pose chunks.  (Not a reference function: nadir_sim only
+    projects the detections of visible frames.)"""
     ctx = _lib.default_context(config.device)
     poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 12)
     counts = np.zeros(poses.shape[0], dtype=np.int32)
