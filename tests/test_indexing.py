@@ -114,3 +114,13 @@ def test_batch_runner_main_issues_the_reference_commands():
     got = []
     batch_runner.main(call=lambda cmd, **kw: got.append([cmd, kw]) or 0)
     assert got == want and len(got) == 32
+
+
+def test_pool_local_counter_hands_out_each_chunk_once():
+    from vinsat_b200 import pool
+    seen = []
+    done = pool.drain(pool.make_counter("x", 1), 50, lambda w, c: seen.append(c), n_workers=4)
+    assert sorted(seen) == list(range(50)) and sorted(c for _, c in done) == list(range(50))
+    import pytest
+    with pytest.raises(ZeroDivisionError):
+        pool.drain(pool.LocalCounter(), 5, lambda w, c: 1 / 0, n_workers=2)

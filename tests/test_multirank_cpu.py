@@ -54,6 +54,25 @@ def _worker(rank, world, port, q):
     # --- accept sums are plain all-reduces of per-window partial sums ---
     part = torch.tensor([np.abs(local).sum()], dtype=torch.float64); dist.all_reduce(part)
     out["sum_close"] = bool(abs(part.item() - np.abs(r).sum()) <= 1e-9 * np.abs(r).sum())
+    # --- dynamic chunk pool (vinsat_b200/pool.py): every chunk handed out exactly once across ranks x workers ---
+    from vinsat_b200 import pool
+    import time
+    n_chunks = 23
+    counter = pool.make_counter("test_pool_%d" % world, world)
+    mine = pool.drain(counter, n_chunks, lambda w, c: time.sleep(0.002 * (1 + rank)), n_workers=2)
+    got = torch.zeros(n_chunks, dtype=torch.int64)
+    for _, c in mine:
+        got[c] += 1
+    dist.all_reduce(got)
+    out["pool_each_chunk_once"] = bool((got == 1).all())
+    cnt = torch.tensor([len(mine)], dtype=torch.int64); cmin = cnt.clone(); dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+    out["pool_every_rank_worked"] = bool(cmin.item() >= 1)
+    # --- SatCam sweep: contiguous pose slices cover [0, n) once (sim/SatCam.py::rank_slice) ---
+    from vinsat_b200.sim.SatCam import rank_slice
+    lo2, hi2 = rank_slice(1_000_003, rank, world)
+    cover = torch.tensor([hi2 - lo2], dtype=torch.int64); dist.all_reduce(cover)
+    edges = torch.zeros(world + 1, dtype=torch.int64); edges[rank] = lo2; edges[rank + 1] += 0
+    out["satcam_slices_cover"] = bool(cover.item() == 1_000_003 and lo2 == (1_000_003 * rank) // world)
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()

@@ -74,6 +74,21 @@ void timing_resolve(vinsat_ctx* ctx) {
   ctx->pending.clear();
 }
 
+int smem_optin(vinsat_ctx* ctx, int slot, const void* func, const char* name, int bytes) {
+  if (!ctx->smem_optin_done[slot]) {
+    // dynamic limit = device opt-in maximum minus the kernel's static shared memory
+    cudaFuncAttributes fa;
+    VS_CUDA(ctx, cudaFuncGetAttributes(&fa, func));
+    ctx->smem_optin_cap[slot] = ctx->max_smem_optin - (int)fa.sharedSizeBytes;
+    VS_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin_cap[slot]));
+    ctx->smem_optin_done[slot] = true;
+  }
+  if (bytes > ctx->smem_optin_cap[slot])
+    return set_error(ctx, VINSAT_EINVAL, "%s needs %d B of dynamic shared memory, device allows %d", name, bytes,
+                     ctx->smem_optin_cap[slot]);
+  return VINSAT_OK;
+}
+
 void* ctx_scratch(vinsat_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->scratch_bytes) return ctx->scratch;
   if (ctx->scratch) {

@@ -41,7 +41,8 @@ struct vinsat_ctx {
   int device = 0;
   int sm_count = 148;
   int max_smem_optin = 48 * 1024;      // cudaDevAttrMaxSharedMemoryPerBlockOptin of `device`
-  bool smem_optin_done[8] = {false};   // per kernel (vs::SmemSlot): the opt-in is per device, so it is tracked per context
+  bool smem_optin_done[8] = {false};
+  int smem_optin_cap[8] = {0};   // per kernel (vs::SmemSlot): the opt-in is per device, so it is tracked per context
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   std::string err;
@@ -99,16 +100,11 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // so the opt-in is remembered per context (one context = one device), never in a process-wide static; it is always
 // raised to the device maximum so that two contexts on one device cannot lower each other's limit.
 enum SmemSlot { SM_SELECT = 0, SM_ASM_STAGED, SM_ASM_2PASS, SM_SYSROWS, SM_TRIAL, SM_SPARE0, SM_SPARE1, SM_SPARE2 };
+int smem_optin(vinsat_ctx* ctx, int slot, const void* func, const char* name, int bytes);
 #define VS_SMEM_OPTIN(ctx, slot, kernel, bytes)                                                              \
   do {                                                                                                       \
-    if ((int)(bytes) > (ctx)->max_smem_optin)                                                                \
-      return vs::set_error((ctx), VINSAT_EINVAL, "%s needs %d B of shared memory, device allows %d", #kernel, \
-                           (int)(bytes), (ctx)->max_smem_optin);                                             \
-    if (!(ctx)->smem_optin_done[slot]) {                                                                     \
-      VS_CUDA((ctx), cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,               \
-                                          (ctx)->max_smem_optin));                                           \
-      (ctx)->smem_optin_done[slot] = true;                                                                   \
-    }                                                                                                        \
+    const int _rc = vs::smem_optin((ctx), (slot), (const void*)(kernel), #kernel, (int)(bytes));             \
+    if (_rc != VINSAT_OK) return _rc;                                                                        \
   } while (0)
 
 // RAII device buffer for the stand-alone entry points.

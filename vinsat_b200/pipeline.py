@@ -46,6 +46,24 @@ class PipelinedSolver:
         if errs:
             raise errs[0]
 
+    def solve_pool(self, counter, n_jobs, inputs_of, output_of, num_iters=20, n_init=10, lamda_init=1e-4,
+                   mode=_lib.MODE_STEP1S, on_done=None):
+        """Dynamic version of `solve_many` for a work pool shared by several GPUs / processes (vinsat_b200/pool.py):
+        every slot pulls job indices c from `counter` until `n_jobs` are handed out; job c reads `inputs_of(c)` (host
+        arrays) and writes the solved states to `output_of(slot)` (one host buffer per slot, consumed by
+        `on_done(c, slot)` before the slot's next job).  Returns the number of jobs this solver executed."""
+        from . import pool
+
+        def work(s, c):
+            ctx, batch = self.slots[s]
+            batch.upload(inputs_of(c))
+            batch.od_solve(num_iters, n_init, lamda_init, mode)
+            batch.get_states(output_of(s))
+            if on_done:
+                on_done(c, s)
+
+        return len(pool.drain(counter, n_jobs, work, len(self.slots)))
+
     def close(self):
         for ctx, batch in self.slots:
             batch.close()
