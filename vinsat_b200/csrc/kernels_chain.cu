@@ -333,8 +333,10 @@ __device__ __forceinline__ void gj_block3_slots(double (&a)[NS][9], const int l,
 
 constexpr int kF3Warps = 1;
 
-template <bool SPIKE, bool FUSED>
-__global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
+// MINB = resident CTAs per SM the register allocation must allow: 8 lets ptxas take 244 registers, 12 caps it at 168
+// (68 bytes of spills in the fused variant) so that three warps share a scheduler when there are enough chains.
+template <bool SPIKE, bool FUSED, int MINB = 8>
+__global__ void __launch_bounds__(kF3Warps * 32, MINB) k_chain_forward3(ChainArgs A) {
   constexpr int NS = SPIKE ? 3 : 2;
   if (A.gate && *A.gate) return;
   __shared__ __align__(16) double s_col[kF3Warps][kCPW][2][3][kMS];
@@ -521,7 +523,13 @@ __global__ void __launch_bounds__(kF3Warps * 32) k_chain_forward3(ChainArgs A) {
 template <bool SPIKE>
 static int launch_forward(vinsat_ctx* ctx, const ChainArgs& A) {
   if (A.fused) {
-    VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<false, true>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
+    static const int minb = getenv("VINSAT_SWEEP_MINB") ? atoi(getenv("VINSAT_SWEEP_MINB")) : 8;
+    if (minb >= 16)
+      VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<false, true, 16>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
+    else if (minb >= 12)
+      VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<false, true, 12>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
+    else
+      VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<false, true, 8>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
   } else {
     VS_LAUNCH(ctx, F_SOLVE, (k_chain_forward3<SPIKE, false>), ceil_div(A.n_chains, kF3Warps * kCPW), kF3Warps * 32, 0, A);
   }
