@@ -149,6 +149,40 @@ int vinsat_batch_od_solve(vinsat_batch* b, int num_iters, int n_init, double lam
 /* JTwJ[:, -9:, -9:] of the last trial of the last iteration (BA_filtering.py:97).  out [P,9,9]. */
 int vinsat_batch_last_hessian(vinsat_batch* b, double* out);
 
+/* ---- (f)1: streaming_version's outer loop (od_pipe.py:987-1060) in one call ------------------------------------
+ * The whole sequence after read_detections / remove_elems (T_all frames incl. knots, M_all observations, `ii` GLOBAL
+ * frame indices, non-decreasing) plus the window schedule: window w covers frames [0, t_final[w]) and observations
+ * [0, i_final[w]) -- the (t_final, i_final) pairs identify_next_batch_new returns (:898-905, integers, computed by
+ * the caller).  Window 0 starts from `states`; the frames a later window adds are seeded on the device by
+ * propagate_dynamics_init (:1011, BA_utils.py:114-129) from the last solved state and the carried `velocities` row
+ * (omega = full-rate compute_omega_from_quat output, [n_omega,3]); every window then runs num_iters BA iterations
+ * (the first n_init_first of window 0 with initialize=1, :1036-1040), starting from lamda_init (:1032).  If the last
+ * window ends before T_all the remaining frames are propagated only (:1046-1060).
+ * Outputs (host): states_out [t_final[W-1],10] solved states of the last window; seed_states_out [T_all,10] nullable
+ * = the state every frame entered its window with (states for window 0, propagated seeds afterwards, tail included);
+ * window_last_state_out [W,10] nullable = last frame's state after each window's solve (:1042); last_hessian_out
+ * [9,9] nullable (BA_filtering.py:97 of the last call). */
+typedef struct {
+  int64_t n_frames, n_obs;
+  const double* states;        /* [T_all,10] */
+  const double* velocities;    /* [T_all,3]  the `velocities` array carried beside the states (od_pipe.py:942) */
+  const double* intrinsics;    /* [T_all,4]  */
+  const double* cum_rot;       /* [T_all,4]  */
+  const int64_t* time_idx;     /* [T_all]    */
+  const double* landmarks_xyz; /* [M_all,3]  */
+  const double* landmarks_uv;  /* [M_all,2]  */
+  const double* confidences;   /* [M_all]    */
+  const int64_t* ii;           /* [M_all]    */
+  int64_t n_omega;
+  const double* omega;         /* [n_omega,3] */
+  int64_t n_windows;
+  const int64_t* t_final;      /* [W] */
+  const int64_t* i_final;      /* [W] */
+} vinsat_stream_desc;
+int vinsat_stream_solve(vinsat_ctx* ctx, const vinsat_stream_desc* desc, int num_iters, int n_init_first,
+                        double lamda_init, int mode, double* states_out, double* seed_states_out,
+                        double* window_last_state_out, double* last_hessian_out);
+
 /* Per-iteration diagnostics of the LAST vinsat_batch_ba_iterate call, for parity tests (host outputs,
  * any may be NULL): r_obs [Mtot,2], weights [Mtot] (after /max and *conf), c_obs [P], D [Ttot,9,9] (without
  * damping), U [Ttot,9,9] (block (i,i+1); last of each problem unused), rhs [Ttot,9], dpose [Ttot,9]. */

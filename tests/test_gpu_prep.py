@@ -83,8 +83,29 @@ def test_attitude_propagate_matches_attitude_step(ctx):
         for k in range(300):
             if k % 3 == 0:
                 assert np.allclose(out[i, k // 3], x, rtol=0, atol=1e-12), (i, k)
-            x = tp.attitude_step(x.copy(), 1.0)
+            x = _host_attitude_step(x.copy(), 1.0)
         assert np.allclose(out[i, 100], x, rtol=0, atol=1e-12)
+
+
+def _host_attitude_step(x, h):
+    """attitude_step (trajgen_pipe.py:198-207) on the host, from the mirror's derivative function."""
+    f = tp.attitude_dynamics
+    f1 = f(x); f2 = f(x + 0.5 * h * f1); f3 = f(x + 0.5 * h * f2); f4 = f(x + h * f3)
+    xn = x + (h / 6.0) * (f1 + 2 * f2 + 2 * f3 + f4)
+    xn[:4] /= np.linalg.norm(xn[:4])
+    return xn
+
+
+def test_single_step_helpers_run_on_device_and_match_reference_goldens(ctx):
+    """trajgen_pipe.orbit_step / attitude_step are one-step device calls: against the reference's own outputs."""
+    from conftest import load_golden
+    g = load_golden("helpers")
+    got = np.stack([tp.orbit_step(x, 1.0) for x in g["x"]])
+    assert np.abs(got - g["step_np"]).max() <= 1e-13 * np.abs(g["step_np"]).max()
+    xa = g["att_traj"][0].copy()
+    for k in range(5):
+        xa = tp.attitude_step(xa.copy(), 1.0)
+        assert np.abs(xa - g["att_traj"][k + 1]).max() < 1e-14
 
 
 def test_generate_new_traj_shapes(ctx):

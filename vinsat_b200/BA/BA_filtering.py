@@ -9,20 +9,34 @@ from .BA_utils import _np, _ctx, _cum_rot_of
 _cache = {}
 
 
-def _batch_for(arrays):
-    """One cached device batch per (T, M): BA() is called 20x per window with the same sizes."""
+def _fingerprint(a):
+    """Cheap identity of a static input: where it lives, its size and its end values.  BA() is called 20x per window
+    with the same observation / frame arrays (od_pipe.py:1036-1040); a changed array changes at least one of these."""
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    return (a.__array_interface__["data"][0], a.shape, a.dtype.str,
+            (float(flat[0]), float(flat[-1]), float(flat[len(flat) // 2])) if len(flat) else ())
+
+
+def _batch_for(arrays, sources):
+    """One cached device batch per (T, M).  Returns (batch, resident): resident=True when every static input is the
+    one already on the device AND `states` is exactly what the previous BA() call returned -- then nothing is
+    uploaded and the iteration continues from the device-resident states (and residuals)."""
     key = (config.device, len(arrays["time_idx"]), len(arrays["ii"]))
-    b = _cache.get(key)
-    if b is None:
+    fp = tuple(_fingerprint(x) for x in sources)
+    ent = _cache.get(key)
+    if ent is None:
         if len(_cache) > 8:
             for old in _cache.values():
-                old.close()
+                old["batch"].close()
             _cache.clear()
-        b = _lib.Batch(_ctx(), arrays)
-        _cache[key] = b
-    else:
-        b.upload(arrays)
-    return b
+        ent = _cache[key] = dict(batch=_lib.Batch(_ctx(), arrays), fp=fp, last=None)
+        return ent, False
+    if ent["fp"] == fp and ent["last"] is not None and np.array_equal(ent["last"], arrays["states"]):
+        return ent, True
+    ent["batch"].upload(arrays)
+    ent["fp"] = fp
+    return ent, False
 
 
 def BA(iter, states, velocities, imu_meas, landmarks, landmarks_xyz, ii, time_idx, intrinsics, confidences,
@@ -51,11 +65,14 @@ def BA(iter, states, velocities, imu_meas, landmarks, landmarks_xyz, ii, time_id
                   time_idx=np.ascontiguousarray(time_idx, dtype=np.int64), landmarks_xyz=np.ascontiguousarray(xyz),
                   landmarks_uv=np.ascontiguousarray(uv), confidences=np.ascontiguousarray(conf),
                   ii=np.ascontiguousarray(ii_np))
-    b = _batch_for(arrays)
+    ent, resident = _batch_for(arrays, (landmarks, landmarks_xyz, confidences, ii, time_idx, intrinsics, imu_meas))
+    b = ent["batch"]
     lam, ntr = b.ba_iterate(int(iter), float(lamda_init), initialize=bool(initialize), mode=config.mode())
     if lam[0] * 100 > 1e4 and ntr[0] >= 8:
         pass   # the reference prints "lamda too large" (:76); kept silent here
-    states_new = torch.from_numpy(b.get_states())[None]
+    new = b.get_states()
+    ent["last"] = new.copy()        # private copy: the caller may modify the tensor it gets back
+    states_new = torch.from_numpy(new)[None]
     last_hessian = torch.from_numpy(b.last_hessian())
     if iter > 18:                                        # :86-87
         gt = _np(poses_gt_eci)

@@ -31,6 +31,13 @@ class ProblemDesc(C.Structure):
                 ("landmarks_uv", c_dp), ("confidences", c_dp), ("ii", c_i64p)]
 
 
+class StreamDesc(C.Structure):
+    _fields_ = [("n_frames", C.c_int64), ("n_obs", C.c_int64), ("states", c_dp), ("velocities", c_dp),
+                ("intrinsics", c_dp), ("cum_rot", c_dp), ("time_idx", c_i64p), ("landmarks_xyz", c_dp),
+                ("landmarks_uv", c_dp), ("confidences", c_dp), ("ii", c_i64p), ("n_omega", C.c_int64), ("omega", c_dp),
+                ("n_windows", C.c_int64), ("t_final", c_i64p), ("i_final", c_i64p)]
+
+
 # name -> (restype, argtypes); every function declared in include/vinsat_b200.h
 SIGNATURES = {
     "vinsat_abi_version": (C.c_int, []),
@@ -70,6 +77,8 @@ SIGNATURES = {
     "vinsat_batch_ba_iterate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vinsat_batch_od_solve": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int]),
     "vinsat_batch_last_hessian": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vinsat_stream_solve": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_int, C.c_int, C.c_double, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vinsat_batch_debug_fetch": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7),
     "vinsat_batch_eval_resjac": (C.c_int, [C.c_void_p]),
     "vinsat_batch_fetch_resjac": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -268,6 +277,30 @@ class Context:
         out = np.empty((x0.shape[0], n_steps // stride + 1, 7))
         self.check(self.lib.vinsat_attitude_propagate(self.h, MEM_HOST, x0.shape[0], int(n_steps), int(stride),
                                                       float(h), _ptr(J), _ptr(x0), _ptr(out)))
+        return out
+
+    def stream_solve(self, states, velocities, intrinsics, cum_rot, time_idx, landmarks_xyz, landmarks_uv, confidences,
+                     ii, omega, t_final, i_final, num_iters=20, n_init_first=10, lamda_init=1e-4, mode=MODE_STEP1S):
+        """streaming_version's window loop (od_pipe.py:987-1060) in one device call; see include/vinsat_b200.h.
+        Returns dict(states (t_final[-1],10), seed_states (T_all,10), window_last_state (W,10), last_hessian (9,9))."""
+        keep = dict(states=f64(states), velocities=f64(velocities), intrinsics=f64(intrinsics), cum_rot=f64(cum_rot),
+                    time_idx=i64(time_idx), xyz=f64(landmarks_xyz), uv=f64(landmarks_uv), conf=f64(confidences), ii=i64(ii),
+                    omega=f64(omega).reshape(-1, 3), t_final=i64(t_final), i_final=i64(i_final))
+        d = StreamDesc()
+        d.n_frames, d.n_obs = keep["states"].shape[0], keep["xyz"].reshape(-1, 3).shape[0]
+        cast = lambda x, t: C.cast(_ptr(x), t)
+        d.states = cast(keep["states"], c_dp); d.velocities = cast(keep["velocities"], c_dp)
+        d.intrinsics = cast(keep["intrinsics"], c_dp); d.cum_rot = cast(keep["cum_rot"], c_dp)
+        d.time_idx = cast(keep["time_idx"], c_i64p); d.landmarks_xyz = cast(keep["xyz"], c_dp)
+        d.landmarks_uv = cast(keep["uv"], c_dp); d.confidences = cast(keep["conf"], c_dp); d.ii = cast(keep["ii"], c_i64p)
+        d.n_omega = keep["omega"].shape[0]; d.omega = cast(keep["omega"], c_dp)
+        d.n_windows = len(keep["t_final"]); d.t_final = cast(keep["t_final"], c_i64p); d.i_final = cast(keep["i_final"], c_i64p)
+        W, T_all, T_last = d.n_windows, d.n_frames, int(keep["t_final"][-1])
+        out = dict(states=np.empty((T_last, 10)), seed_states=np.empty((T_all, 10)), window_last_state=np.empty((W, 10)),
+                   last_hessian=np.zeros((9, 9)))
+        self.check(self.lib.vinsat_stream_solve(self.h, C.byref(d), int(num_iters), int(n_init_first), float(lamda_init),
+                                                int(mode), _ptr(out["states"]), _ptr(out["seed_states"]),
+                                                _ptr(out["window_last_state"]), _ptr(out["last_hessian"])))
         return out
 
     def satcam_project(self, poses, landmarks_ecef, hfov, w_px, h_px, want_uv=True, want_mask=True,

@@ -13,6 +13,14 @@ namespace {
 template <typename T>
 int dev_alloc(vinsat_ctx* ctx, T** p, int64_t n) {
   if (n < 1) n = 1;
+  if (ctx->arena_on) {
+    const size_t bytes = ((size_t)n * sizeof(T) + 255) & ~(size_t)255;
+    if (ctx->arena_off + bytes > ctx->arena_bytes)
+      return set_error(ctx, VINSAT_ENOMEM, "batch arena of %zu bytes exhausted", ctx->arena_bytes);
+    *p = (T*)(ctx->arena + ctx->arena_off);
+    ctx->arena_off += bytes;
+    return VINSAT_OK;
+  }
   cudaError_t e = cudaMalloc((void**)p, (size_t)n * sizeof(T));
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -30,15 +38,17 @@ int dev_alloc(vinsat_ctx* ctx, T** p, int64_t n) {
 
 void free_all(vinsat_batch* b) {
   void* ptrs[] = {b->st, b->st_new, b->intr, b->crot, b->gap, b->fprob, b->dyn_order, b->obs_start, b->grec, b->drec, b->mrec,
-                  b->srec, b->wrec, b->delta, b->e_obs, b->e_dyn, b->X, b->uv, b->conf, b->oframe, b->r, b->r_next, b->wu, b->J,
+                  b->srec, b->wrec, b->delta, b->e_obs, b->e_dyn, b->X, b->uv, b->conf, b->oframe, b->r, b->r_next, b->wu,
                   b->d_frame_off, b->d_obs_off, b->c_obs, b->wmax, b->lam, b->lam_next, b->lam32_last, b->init_res,
                   b->active, b->ntrials, b->sel_prefix, b->sel_rank, b->sel_hist, b->flags, b->seg_a, b->seg_b,
                   b->seg_left, b->seg_prob, b->seg_has_next, b->pl_a, b->pl_b, b->pl_prob, b->red_a, b->red_b,
                   b->bb_a, b->bb_e, b->bb_dir, b->bb_prob, b->bb_mid, b->midrec,
                   b->redrec, b->rsys, b->rlow, b->rwrec, b->la_pack, b->la_gath, b->la_rsys, b->la_rlow, b->la_rwrec,
                   b->la_xsep, b->la_sums, b->la_edge, b->la_edges_all, b->la_chain};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  if (!b->in_arena)
+    for (void* p : ptrs)
+      if (p) cudaFree(p);
+  if (b->J) cudaFree(b->J);            // allocated lazily with cudaMalloc, never from the arena
   for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   b->graphs.clear();
   if (b->h_flags) cudaFreeHost(b->h_flags);
@@ -255,6 +265,7 @@ static int create_impl(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t ow
   VS_CUDA(ctx, cudaSetDevice(ctx->device));
   vinsat_batch* b = new vinsat_batch();
   b->ctx = ctx;
+  b->in_arena = ctx->arena_on;
   if (n_segments > 0) {
     if (d->n_problems != 1 || own_lo < 0 || own_hi <= own_lo || own_hi > d->frame_off[1] || own_lo > 1 ||
         own_hi < d->frame_off[1] - 1) {
@@ -659,17 +670,11 @@ int vinsat_batch_last_hessian(vinsat_batch* b, double* out) {
   if (!b->have_iter) return set_error(ctx, VINSAT_EINVAL, "no BA iteration has run on this batch");
   VS_CUDA(ctx, cudaSetDevice(ctx->device));
   VS_TRY(ensure_srec(b));
-  std::vector<double> l32(b->P);
-  VS_CUDA(ctx, cudaMemcpyAsync(l32.data(), b->lam32_last, b->P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  for (int64_t p = 0; p < b->P; p++) {
-    const int64_t fl = b->frame_off[p + 1] - 1;
-    if (fl < b->frame_off[p]) { memset(out + p * 81, 0, 81 * sizeof(double)); continue; }
-    VS_CUDA(ctx, cudaMemcpyAsync(out + p * 81, b->srec + fl * VS_SREC, 81 * sizeof(double), cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-  }
+  double* d_out = (double*)ctx_scratch(ctx, (size_t)b->P * 81 * sizeof(double));
+  if (!d_out) return set_error(ctx, VINSAT_ENOMEM, "scratch allocation failed");
+  VS_TRY(launch_gather_last_hessian(b, d_out));          // JTwJ includes eye*lamda (:54,97)
+  VS_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)b->P * 81 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  for (int64_t p = 0; p < b->P; p++)
-    for (int k = 0; k < 9; k++) out[p * 81 + k * 10] += l32[p];      // JTwJ includes eye*lamda (:54,97)
   return VINSAT_OK;
 }
 
@@ -715,7 +720,13 @@ int vinsat_batch_eval_resjac(vinsat_batch* b) {
   if (!b) return set_error(nullptr, VINSAT_EINVAL, "vinsat_batch_eval_resjac: NULL batch");
   vinsat_ctx* ctx = b->ctx;
   VS_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (!b->J) VS_TRY(dev_alloc(ctx, &b->J, b->M * 12));
+  if (!b->J) {
+    const bool arena = ctx->arena_on;      // J outlives any arena: always a plain allocation
+    ctx->arena_on = false;
+    const int rc = dev_alloc(ctx, &b->J, b->M * 12);
+    ctx->arena_on = arena;
+    if (rc != VINSAT_OK) return rc;
+  }
   return launch_resjac(b);
 }
 
@@ -738,6 +749,120 @@ int vinsat_batch_fetch_resjac(vinsat_batch* b, double* r_out, double* J_out) {
     VS_CUDA(ctx, cudaMemcpyAsync(J_out, tmp, M * 12 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  return VINSAT_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// (f)1: streaming_version's outer loop on the device (od_pipe.py:987-1060).
+// The window schedule (integers from identify_next_batch_new, :898-905) comes from the host; everything between
+// "window w starts" and "window w is solved" runs here without handing states back: the new frames are seeded by
+// propagate_dynamics_init (:1011, BA_utils.py:114-129) from the last solved state, the window's num_iters BA calls run
+// back to back (:1035-1040; the host only polls the pinned LM-trial counter), and the solved states stay in device
+// memory for the next window.  Windows always start at frame 0 and grow (:994-1000,1015-1023), so every window's batch
+// is carved out of ONE arena sized for the last window.
+// ---------------------------------------------------------------------------------------------------------------
+int vinsat_stream_solve(vinsat_ctx* ctx, const vinsat_stream_desc* d, int num_iters, int n_init_first, double lamda_init,
+                        int mode, double* states_out, double* seed_states_out, double* window_last_state_out,
+                        double* last_hessian_out) {
+  VS_CHECK_ARG(ctx, ctx != nullptr && d != nullptr);
+  VS_CHECK_ARG(ctx, mode == VINSAT_MODE_STEP1S || mode == VINSAT_MODE_SKIP100);
+  VS_CHECK_ARG(ctx, d->n_frames >= 1 && d->n_obs >= 0 && d->n_windows >= 1 && d->t_final && d->i_final);
+  VS_CHECK_ARG(ctx, d->states && d->velocities && d->intrinsics && d->cum_rot && d->time_idx && states_out);
+  VS_CHECK_ARG(ctx, d->n_obs == 0 || (d->landmarks_xyz && d->landmarks_uv && d->confidences && d->ii));
+  VS_CHECK_ARG(ctx, num_iters >= 0 && lamda_init >= 1e-10);
+  VS_CHECK_ARG(ctx, !ctx->arena_on);
+  const int64_t T_all = d->n_frames, W = d->n_windows;
+  for (int64_t w = 0; w < W; w++) {
+    VS_CHECK_ARG(ctx, d->t_final[w] >= 1 && d->t_final[w] <= T_all && d->i_final[w] >= 0 && d->i_final[w] <= d->n_obs);
+    VS_CHECK_ARG(ctx, w == 0 || (d->t_final[w] > d->t_final[w - 1] && d->i_final[w] >= d->i_final[w - 1]));
+  }
+  const int64_t T_last = d->t_final[W - 1], M_last = d->i_final[W - 1];
+  const bool tail = T_last < T_all;                       // od_pipe.py:1046: frames after the last window are propagated only
+  const int64_t span = d->time_idx[T_all - 1] - d->time_idx[0];
+  VS_CHECK_ARG(ctx, span >= 0 && span < (1ll << 31));
+  if (W > 1 || tail) VS_CHECK_ARG(ctx, d->omega && d->n_omega >= d->time_idx[(tail ? T_all : T_last) - 1]);
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->stream;
+  // persistent device state across windows
+  DevBuf<double> st_carry, vel_carry, seed, chain, omega, win_last;
+  DevBuf<int64_t> tidx;
+  VS_CUDA(ctx, st_carry.alloc(T_all * 10));
+  VS_CUDA(ctx, vel_carry.alloc(T_all * 3));
+  VS_CUDA(ctx, seed.alloc(T_all * 10));
+  VS_CUDA(ctx, chain.alloc((span + 2) * 10));
+  VS_CUDA(ctx, omega.alloc(std::max<int64_t>(d->n_omega, 1) * 3));
+  VS_CUDA(ctx, win_last.alloc(W * 10));
+  VS_CUDA(ctx, tidx.alloc(T_all));
+  VS_CUDA(ctx, cudaMemcpyAsync(vel_carry.p, d->velocities, T_all * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  VS_CUDA(ctx, cudaMemcpyAsync(seed.p, d->states, T_all * 10 * sizeof(double), cudaMemcpyHostToDevice, s));
+  VS_CUDA(ctx, cudaMemcpyAsync(tidx.p, d->time_idx, T_all * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  if (d->n_omega > 0 && d->omega)
+    VS_CUDA(ctx, cudaMemcpyAsync(omega.p, d->omega, d->n_omega * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+  // one arena for every window's batch, sized for the last (largest) window
+  {
+    const int64_t nseg = (int64_t)sqrt((double)T_last) + 2;
+    const size_t need = (size_t)T_last * 4600 + (size_t)M_last * 104 + (size_t)nseg * 6400 + (1u << 20);
+    if (ctx->arena_bytes < need) {
+      if (ctx->arena) { cudaStreamSynchronize(s); cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
+      VS_CUDA(ctx, cudaMalloc((void**)&ctx->arena, need));
+      ctx->arena_bytes = need;
+    }
+  }
+  const int64_t frame_off[2] = {0, 0}, obs_off[2] = {0, 0};
+  int rc = VINSAT_OK;
+  int64_t T_prev = 0;
+  for (int64_t w = 0; w < W && rc == VINSAT_OK; w++) {
+    const int64_t Tw = d->t_final[w], Mw = d->i_final[w];
+    int64_t fo[2] = {frame_off[0], Tw}, oo[2] = {obs_off[0], Mw};
+    vinsat_problem_desc pd;
+    pd.n_problems = 1;
+    pd.frame_off = fo; pd.obs_off = oo;
+    pd.states = d->states; pd.intrinsics = d->intrinsics; pd.cum_rot = d->cum_rot; pd.time_idx = d->time_idx;
+    pd.landmarks_xyz = d->landmarks_xyz; pd.landmarks_uv = d->landmarks_uv; pd.confidences = d->confidences; pd.ii = d->ii;
+    vinsat_batch* b = nullptr;
+    ctx->arena_off = 0;
+    ctx->arena_on = true;
+    rc = create_impl(ctx, &pd, 0, 0, 0, &b);
+    ctx->arena_on = false;
+    if (rc != VINSAT_OK) break;
+    auto step = [&]() -> int {
+      if (w > 0) {
+        // seed the new frames: chain from the last solved state with the carried `velocities` row (the reference passes
+        // velocities_t[:, -1], not the state's own velocity, :1011), tdiff + duration steps of 1 s
+        const int64_t t0 = d->time_idx[T_prev - 1];
+        const int64_t n_steps = d->time_idx[Tw - 1] - t0;
+        VS_TRY(launch_chain(ctx, n_steps, 1.0, st_carry.p + (T_prev - 1) * 10, vel_carry.p + (T_prev - 1) * 3,
+                            omega.p + t0 * 3, chain.p));
+        VS_CUDA(ctx, cudaMemcpyAsync(b->st, st_carry.p, T_prev * 10 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        VS_TRY(launch_stream_gather(ctx, Tw - T_prev, chain.p, tidx.p, T_prev, t0, b->st, vel_carry.p, seed.p));
+      }
+      VS_TRY(vinsat_batch_od_solve(b, num_iters, w == 0 ? n_init_first : 0, lamda_init, mode));
+      VS_CUDA(ctx, cudaMemcpyAsync(st_carry.p, b->st, Tw * 10 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      VS_CUDA(ctx, cudaMemcpyAsync(win_last.p + w * 10, b->st + (Tw - 1) * 10, 10 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      if (w == W - 1 && last_hessian_out && num_iters > 0) VS_TRY(vinsat_batch_last_hessian(b, last_hessian_out));
+      return VINSAT_OK;
+    };
+    rc = step();
+    cudaStreamSynchronize(s);          // the arena is recycled by the next window
+    free_all(b);
+    delete b;
+    T_prev = Tw;
+  }
+  if (rc != VINSAT_OK) return rc;
+  if (tail) {
+    const int64_t t0 = d->time_idx[T_last - 1];
+    const int64_t n_steps = d->time_idx[T_all - 1] - t0;
+    VS_TRY(launch_chain(ctx, n_steps, 1.0, st_carry.p + (T_last - 1) * 10, vel_carry.p + (T_last - 1) * 3, omega.p + t0 * 3,
+                        chain.p));
+    VS_TRY(launch_stream_gather(ctx, T_all - T_last, chain.p, tidx.p, T_last, t0, nullptr, vel_carry.p, seed.p));
+  }
+  VS_CUDA(ctx, cudaMemcpyAsync(states_out, st_carry.p, T_last * 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (seed_states_out)
+    VS_CUDA(ctx, cudaMemcpyAsync(seed_states_out, seed.p, T_all * 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (window_last_state_out)
+    VS_CUDA(ctx, cudaMemcpyAsync(window_last_state_out, win_last.p, W * 10 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  VS_CUDA(ctx, cudaStreamSynchronize(s));
   return VINSAT_OK;
 }
 

@@ -100,6 +100,7 @@ struct vinsat_batch {
   double* la_edge = nullptr;          // [2][10] new states of the first / last owned frame
   double* la_edges_all = nullptr;     // [n_ranks][2][10]
   int32_t* la_chain = nullptr;        // {0, S_total, 0}
+  bool in_arena = false;       // device buffers come from ctx->arena (never cudaFree'd individually)
   bool have_iter = false;
   bool srec_valid = false;
   double last_sigma = 0.0;

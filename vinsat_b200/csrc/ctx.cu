@@ -198,6 +198,7 @@ int vinsat_ctx_destroy(vinsat_ctx* ctx) {
   timing_resolve(ctx);
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;

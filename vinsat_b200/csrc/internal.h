@@ -57,6 +57,10 @@ struct vinsat_ctx {
   size_t scratch_bytes = 0;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // bump arena for batches that are created and destroyed in a loop (vinsat_stream_solve): one cudaMalloc for all windows
+  char* arena = nullptr;
+  size_t arena_bytes = 0, arena_off = 0;
+  bool arena_on = false;
 };
 
 namespace vs {

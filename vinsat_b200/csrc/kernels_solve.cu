@@ -698,4 +698,54 @@ int launch_gate_publish(vinsat_batch* b) {
   return VINSAT_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// JTwJ[:, -9:, -9:] of every problem in one pass (BA_filtering.py:97): D block of the problem's last frame plus the
+// float32 damping on the diagonal, gathered into out[P][81] on the device (one D2H copy instead of one per problem).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gather_last_hessian(int64_t P, const int64_t* __restrict__ frame_off,
+                                                             const double* __restrict__ srec,
+                                                             const double* __restrict__ lam32, double* __restrict__ out) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t p = t / 81;
+  const int k = (int)(t % 81);
+  if (p >= P) return;
+  const int64_t fl = frame_off[p + 1] - 1;
+  double v = 0.0;
+  if (fl >= frame_off[p]) v = srec[fl * VS_SREC + k] + ((k % 10 == 0) ? lam32[p] : 0.0);
+  out[p * 81 + k] = v;
+}
+
+int launch_gather_last_hessian(vinsat_batch* b, double* out_dev) {
+  vinsat_ctx* ctx = b->ctx;
+  VS_LAUNCH(ctx, F_LAYOUT, k_gather_last_hessian, ceil_div(b->P * 81, 128), 128, 0, b->P, b->d_frame_off, b->srec,
+            b->lam32_last, out_dev);
+  return VINSAT_OK;
+}
+
+// Streaming windows (od_pipe.py:1011-1019): frame f of the new window takes the state the chain reached at its time,
+// states_prop[:, time_idx_prop - time_idx_prop[0]]; chain row k is the state k seconds after the chain start t0.
+__global__ void __launch_bounds__(128) k_stream_gather(int64_t n, const double* __restrict__ chain,
+                                                       const int64_t* __restrict__ time_idx, int64_t f0, int64_t t0,
+                                                       double* __restrict__ st, double* __restrict__ vel,
+                                                       double* __restrict__ seed) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double* c = chain + (time_idx[f0 + j] - t0) * 10;
+#pragma unroll
+  for (int k = 0; k < 10; k++) {
+    const double v = c[k];
+    if (st) st[(f0 + j) * 10 + k] = v;
+    seed[(f0 + j) * 10 + k] = v;
+  }
+  vel[(f0 + j) * 3] = c[7]; vel[(f0 + j) * 3 + 1] = c[8]; vel[(f0 + j) * 3 + 2] = c[9];
+}
+
+int launch_stream_gather(vinsat_ctx* ctx, int64_t n, const double* chain, const int64_t* time_idx, int64_t f0, int64_t t0,
+                         double* st, double* vel, double* seed) {
+  if (n <= 0) return VINSAT_OK;
+  VS_LAUNCH(ctx, F_LAYOUT, k_stream_gather, ceil_div(n, 128), 128, 0, n, chain, time_idx, f0, t0, st, vel, seed);
+  return VINSAT_OK;
+}
+
 }  // namespace vs

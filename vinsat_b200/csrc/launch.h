@@ -52,6 +52,9 @@ int launch_solve_retract(vinsat_batch* b, int initialize);
 int launch_solve_init_only(vinsat_batch* b);
 int launch_retract_only(vinsat_batch* b);
 int launch_accept(vinsat_batch* b, int initialize, double Sigma);
+int launch_gather_last_hessian(vinsat_batch* b, double* out_dev);    // out[P][81] = JTwJ[-9:, -9:] incl. damping
+int launch_stream_gather(vinsat_ctx* ctx, int64_t n, const double* chain, const int64_t* time_idx, int64_t f0, int64_t t0,
+                         double* st, double* vel, double* seed);
 
 // ---- kernels_chain.cu -------------------------------------------------------------------------------
 int launch_chain_solve(vinsat_batch* b);   // delta = A^-1 rhs for every active problem (partitioned block LU)

@@ -153,3 +153,38 @@ def oe2eci_values(a, e, i, Omega, omega, nu, mu=MU):
         R1, R2, R3 = rotz(Omega), rotx(i), rotz(omega)
     R = np.dot(R1, np.dot(R2, R3))
     return np.concatenate([np.dot(R, r_peri), np.dot(R, v_peri)])
+
+
+# ---- right-hand sides used by trajgen_pipe's single-state helpers (trajgen_pipe.py:130-143,185-196) -------------------
+_J2_ROWS = np.array([[6.0, -1.5, -1.5], [6.0, -1.5, -1.5], [3.0, -4.5, -4.5]])
+
+
+def orbit_rhs(x, mu=MU, j2=J2C):
+    """[v, a(r)] for the 6-state: a = -mu r/|r|^3 + j2/|r|^7 (C r.^2) .* r with the reference's coefficient rows."""
+    r, v = x[:3], x[3:6]
+    n = np.linalg.norm(r)
+    return np.concatenate([v, -(mu / n ** 3) * r + (j2 / n ** 7) * np.dot(_J2_ROWS, r ** 2) * r])
+
+
+def hat(v):
+    """hat(v) w = v x w."""
+    out = np.zeros((3, 3))
+    out[0, 1], out[0, 2], out[1, 2] = -v[2], v[1], -v[0]
+    return out - out.T
+
+
+def quat_left_matrix_wxyz(q):
+    """4x4 M with q (x) p = M p for scalar-FIRST quaternions: [[s, -v^T], [v, s I + hat(v)]]."""
+    s, v = q[0], q[1:]
+    M = np.empty((4, 4))
+    M[0, 0], M[0, 1:], M[1:, 0] = s, -v, v
+    M[1:, 1:] = s * np.eye(3) + hat(v)
+    return M
+
+
+def attitude_rhs(x, J):
+    """[q_dot, omega_dot] of a torque-free rigid body with inertia J (scalar-first quaternion, already unit norm)."""
+    q, w = x[:4], x[4:]
+    q_dot = 0.5 * quat_left_matrix_wxyz(q)[:, 1:] @ w
+    w_dot = -np.linalg.solve(J, np.cross(w, J @ w))
+    return np.hstack((q_dot, w_dot))

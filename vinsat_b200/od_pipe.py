@@ -123,34 +123,27 @@ def visibility_mask(landmark_uv_proj, landmarks_uv, confidence):
             * ((p - landmarks_uv[None]).norm(dim=-1) < 1000) * (torch.as_tensor(confidence) > 0.8))[0]
 
 
-def _window_solve(states_t, cum_rot, landmarks_uv, landmarks_xyz, ii_t, time_idx_t, intrinsics_t, confidences,
-                  lamda_init, num_iters, n_init, poses_gt_eci_t):
-    """The `for iter in range(num_iters): BA(...)` loop of one window (od_pipe.py:1035-1040) on the device:
-    one upload, num_iters batched-BA calls, one download."""
-    T, M = states_t.shape[1], len(ii_t)
-    arrays = dict(frame_off=np.array([0, T], dtype=np.int64), obs_off=np.array([0, M], dtype=np.int64),
-                  states=np.ascontiguousarray(states_t[0].numpy()), intrinsics=np.ascontiguousarray(intrinsics_t[0].numpy()),
-                  cum_rot=np.ascontiguousarray(cum_rot), time_idx=np.ascontiguousarray(time_idx_t, dtype=np.int64),
-                  landmarks_xyz=np.ascontiguousarray(landmarks_xyz[0].numpy()),
-                  landmarks_uv=np.ascontiguousarray(landmarks_uv[0].numpy()),
-                  confidences=np.ascontiguousarray(confidences.numpy()), ii=np.ascontiguousarray(ii_t, dtype=np.int64))
-    b = _lib.Batch(_ctx(), arrays)
-    lam = float(lamda_init)
-    for it in range(num_iters):
-        lam_arr, _ = b.ba_iterate(it, lam, initialize=(it < n_init), mode=config.mode())
-        lam = float(lam_arr[0])
-        if it > 18:                                            # BA_filtering.py:86-87
-            s = b.get_states()
-            d = np.abs(s[:, :3] - poses_gt_eci_t[:, :3].numpy()).mean(axis=0)
-            print("final pos: ", torch.from_numpy(d), float(np.linalg.norm(d)))
-    states_new = torch.from_numpy(b.get_states())[None]
-    last_hessian = torch.from_numpy(b.last_hessian())
-    b.close()
-    return states_new, lam, last_hessian
+def window_schedule(ii, time_idx):
+    """The (t_final, i_final) pairs the `while not seq_end` loop of od_pipe.py:987-992 visits, by repeated
+    identify_next_batch_new (:898-905) -- integers only, bit-exact by construction."""
+    t = i = 0
+    seq_end = False
+    t_final, i_final = [], []
+    while not seq_end:
+        t, i, seq_end = identify_next_batch_new(ii, time_idx, i, t)
+        t_final.append(int(t))
+        i_final.append(int(i))
+    return np.array(t_final, dtype=np.int64), np.array(i_final, dtype=np.int64)
 
 
 def streaming_version(detections=None, orbit_np=None, orbit_file_name=None, detections_file_name=None):
-    """od_pipe.py:911-1062.  Returns (errors, first_detection, times)."""
+    """od_pipe.py:911-1062.  Returns (errors, first_detection, times).
+
+    Host part = the reference's own preprocessing (ingest, ground truth, visibility mask, remove_elems, initial guess
+    with the reference's RNG call order).  The window loop (:987-1060) is ONE device call, `vinsat_stream_solve`: the
+    growing-window schedule is precomputed here (integers), the device seeds every window's new frames with
+    propagate_dynamics_init, runs the 20 BA iterations per window and keeps the solved states resident.  The error /
+    time lists are then assembled from the states the call returns, in the order the reference appends them."""
     seeding(0)
     h = 1
     dt = 1 / h
@@ -176,8 +169,7 @@ def streaming_version(detections=None, orbit_np=None, orbit_file_name=None, dete
 
     # initial guess (od_pipe.py:941-973); the torch RNG call order is the reference's
     T = len(gt_pos_eci)
-    N = max(time_idx[1:] - time_idx[:-1])
-    velocities = gt_vel_eci[time_idx].unsqueeze(0).double()
+    velocities = gt_vel_eci[time_idx].double()
     # od_pipe.py:944-953 (compute_omega_from_quat, zero-padded omegas (1,T,N,3), precompute_cum_rotations) as one
     # device call that returns the only slice `predict` reads, cum_rotations[0, :, -1]
     cum_rot, gt_omega = cum_rotations_from_quat(gt_quat_eci_full, time_idx, dt)
@@ -186,65 +178,28 @@ def streaming_version(detections=None, orbit_np=None, orbit_file_name=None, dete
     velocity_offset = torch.randn([T, 3]) * velocities.abs().mean() * 0.1
     position = poses_gt_eci.double()[:, :3] + position_offset
     orientation = quaternion_exp(quaternion_log(poses_gt_eci.double()[:, 3:]) + orientation_offset)
-    vels = velocities.double() + velocity_offset.unsqueeze(0)
-    poses = torch.cat([position, orientation], dim=1).unsqueeze(0)
-    states = torch.cat([poses, vels], dim=-1)
-    landmarks_uv = landmarks_uv.unsqueeze(0)
-    landmarks_xyz = landmarks_xyz.unsqueeze(0)
-    intrinsics = intrinsics.unsqueeze(0)
-    lamda_init = 1e-4
+    states = torch.cat([position, orientation, velocities + velocity_offset], dim=-1)
 
-    t = 0
-    i = 0
-    seq_end = False
-    patch_id = 0
+    t_final, i_final = window_schedule(ii, time_idx)
+    out = _ctx().stream_solve(states.numpy(), velocities.numpy(), intrinsics.double().numpy(), cum_rot, time_idx,
+                              landmarks_xyz.double().numpy(), landmarks_uv.double().numpy(), confidences.numpy(), ii,
+                              gt_omega.double().numpy(), t_final, i_final, num_iters=num_iters, n_init_first=10,
+                              lamda_init=1e-4, mode=config.mode())
+    seed = torch.from_numpy(out["seed_states"])
+    win_last = torch.from_numpy(out["window_last_state"])
+    gt = poses_gt_eci.double()
     errors, times = [], []
-    first_detection = None
-    while not seq_end:                                         # od_pipe.py:987
-        t_init, i_init = t, i
-        t_final, i_final, seq_end = identify_next_batch_new(ii, time_idx, i, t)
-        t, i = t_final, i_final
-        if patch_id == 0:
-            states_t = states[:, :t_final]
-            velocities_t = velocities[:, :t_final]
-            time_idx_t = time_idx[:t_final]
-            poses_gt_eci_t = poses_gt_eci[:t_final]
-            first_detection = time_idx_t[-1]
-        else:
-            omega = gt_omega[time_idx[t_init - 1]:time_idx[t_final - 1]].unsqueeze(0).double()
-            tdiff = time_idx[t_init] - time_idx[t_init - 1]
-            duration = time_idx[t_final - 1] - time_idx[t_init]
-            states_prop, velocities_prop, _, _ = propagate_dynamics_init(states_t[:, -1], velocities_t[:, -1], omega,
-                                                                         int(tdiff), int(duration), 1)
-            time_idx_prop = time_idx[t_init:t_final]
-            sel = time_idx_prop - time_idx_prop[0]
-            states_prop, velocities_prop = states_prop[:, sel], velocities_prop[:, sel]
-            time_idx_t = time_idx[:t_final]
-            poses_gt_eci_t = poses_gt_eci[:t_final]
-            states_t = torch.cat([states_t, states_prop], dim=1)
-            velocities_t = torch.cat([velocities_t, velocities_prop], dim=1)
-            error_prop = compute_residuals(states_prop[0][:, :3], poses_gt_eci_t[-states_prop.shape[1]:, :3])[:-1]
-            times.append(time_idx_t[-states_prop.shape[1]:][:-1])
-            errors.append(error_prop)
-        states_t, _, _ = _window_solve(states_t, cum_rot[:t_final], landmarks_uv[:, :i_final], landmarks_xyz[:, :i_final],
-                                       ii[:i_final], time_idx_t, intrinsics[:, :t_final], confidences[:i_final],
-                                       lamda_init, num_iters, 10 if patch_id == 0 else 0, poses_gt_eci_t)
-        patch_id += 1
-        error_t = (states_t[..., :3].reshape(-1, 3)[-1:] - poses_gt_eci_t[-1:, :3]).norm(dim=-1)
-        errors.append(error_t)
-        times.append(time_idx_t[-1:])
-        if seq_end and t_final < len(time_idx):                # od_pipe.py:1046-1060
-            t_init = t_final
-            t_final = len(time_idx)
-            omega = gt_omega[time_idx[t_init - 1]:time_idx[t_final - 1]].unsqueeze(0).double()
-            tdiff = time_idx[t_init] - time_idx[t_init - 1]
-            duration = time_idx[t_final - 1] - time_idx[t_init]
-            states_prop, _, _, _ = propagate_dynamics_init(states_t[:, -1], velocities_t[:, -1], omega, int(tdiff),
-                                                           int(duration), 1)
-            time_idx_prop = time_idx[t_init:t_final]
-            states_prop = states_prop[:, time_idx_prop - time_idx_prop[0]]
-            poses_gt_eci_tail = poses_gt_eci[t_init:t_final]
-            errors.append(compute_residuals(states_prop[0][:, :3], poses_gt_eci_tail[-states_prop.shape[1]:, :3]))
-            times.append(time_idx[-states_prop.shape[1]:])
+    first_detection = time_idx[t_final[0] - 1]
+    for w, tf in enumerate(t_final):
+        if w > 0:                                              # error of the propagated seeds, last one dropped (:1023-1026)
+            ti = t_final[w - 1]
+            errors.append(compute_residuals(seed[ti:tf, :3], gt[ti:tf, :3])[:-1])
+            times.append(time_idx[ti:tf][:-1])
+        errors.append((win_last[w:w + 1, :3] - gt[tf - 1:tf, :3]).norm(dim=-1))        # :1042-1044
+        times.append(time_idx[tf - 1:tf])
+    if t_final[-1] < len(time_idx):                            # :1046-1060: propagate to the end of the sequence
+        ti = t_final[-1]
+        errors.append(compute_residuals(seed[ti:, :3], gt[ti:, :3]))
+        times.append(time_idx[ti:])
     errors = torch.cat(errors)
     return errors, first_detection, times

@@ -1,7 +1,7 @@
 """Mirror of ``estimation/trajgen_pipe.py`` (identical in ``sim/orbit_gen.py:13-207``): orbital elements,
-two-body+J2 orbit dynamics / RK4 step, rigid-body attitude step, trajectory generation.  Single-state
-helpers are NumPy (they are 6- and 7-vectors); whole trajectories run on the device
-(``vinsat_orbit_propagate``, a11 of SURVEY.md section 8).  Citations: estimation/trajgen_pipe.py:line.
+two-body+J2 orbit dynamics / RK4 step, rigid-body attitude step, trajectory generation.  The RK4 steps and whole
+trajectories run on the device (``vinsat_orbit_propagate`` / ``vinsat_attitude_propagate``, a11 of SURVEY.md section 8);
+the derivative functions are thin views of ``hostmath``.  Citations: estimation/trajgen_pipe.py:line.
 """
 import numpy as np
 
@@ -20,19 +20,16 @@ def oe2eci(oe, mu=398600.4418):                                 # :13-44
 
 
 def orbit_dynamics(x_orbit, mu=398600.4418, J2=1.75553e10):     # :130-143
-    r = x_orbit[:3]
-    v = x_orbit[3:6]
-    r_mat = np.array([[6, -1.5, -1.5], [6, -1.5, -1.5], [3, -4.5, -4.5]])
-    v_dot = -(mu / np.linalg.norm(r) ** 3) * r + (J2 / np.linalg.norm(r) ** 7) * np.dot(r_mat, r ** 2) * r
-    return np.concatenate([v, v_dot])
+    """d/dt [r, v] with the reference's two-body + J2 acceleration (non-textbook coefficient rows 6,-1.5,-1.5 /
+    6,-1.5,-1.5 / 3,-4.5,-4.5, SURVEY 0.7): a = -mu r/|r|^3 + J2/|r|^7 (C r^2) .* r.  Host helper for single states;
+    trajectories go through `propagate_orbits` (device)."""
+    x = np.asarray(x_orbit, dtype=np.float64)
+    return hm.orbit_rhs(x[:6], mu, J2)
 
 
 def orbit_step(xk, h):                                          # :145-152
-    f1 = orbit_dynamics(xk)
-    f2 = orbit_dynamics(xk + 0.5 * h * f1)
-    f3 = orbit_dynamics(xk + 0.5 * h * f2)
-    f4 = orbit_dynamics(xk + h * f3)
-    return xk + (h / 6.0) * (f1 + 2 * f2 + 2 * f3 + f4)
+    """One classic RK4 step of the 6-state, on the device (`vinsat_orbit_propagate` with one trajectory, one step)."""
+    return propagate_orbits(np.asarray(xk, dtype=np.float64)[None, :6], 1, float(h))[0, 1]
 
 
 def propagate_orbits(x0, n_steps, h=1.0, stride=1):
@@ -43,41 +40,34 @@ def propagate_orbits(x0, n_steps, h=1.0, stride=1):
 # ---- attitude (3U CubeSat), :155-207 ------------------------------------------------------------------
 m = 4.0
 J = np.diag([(m / 12) * (.1 ** 2 + .34 ** 2), (m / 12) * (.1 ** 2 + .34 ** 2), (m / 12) * (.1 ** 2 + .1 ** 2)])
+_J_DEFAULT = (1 / 3) * np.array([(.1 ** 2 + .34 ** 2), (.1 ** 2 + .34 ** 2), (.1 ** 2 + .1 ** 2)])    # :185 default argument
+H = np.vstack([np.zeros((1, 3)), np.eye(3)])                    # :172
 
 
-def hat(v):
-    return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+def hat(v):                                                     # :160-163: cross-product matrix, hat(v) w = v x w
+    return hm.hat(np.asarray(v, dtype=np.float64))
 
 
-def L(q):
-    s, v = q[0], q[1:]
-    return np.concatenate([np.concatenate([[s], -v.T])[None], np.concatenate([v[:, None], s * np.eye(3) + hat(v)], axis=1)], axis=0)
+def L(q):                                                       # :165-168: left-multiplication matrix, scalar-first q
+    return hm.quat_left_matrix_wxyz(np.asarray(q, dtype=np.float64))
 
 
-H = np.concatenate([np.zeros((1, 3)), np.eye(3)], axis=0)
+def G(q):                                                       # :177-178
+    return L(q)[:, 1:]
 
 
-def G(q):
-    return L(q) @ H
-
-
-def attitude_dynamics(x_attitude, J=np.diag((1 / 3) * np.array([(.1 ** 2 + .34 ** 2), (.1 ** 2 + .34 ** 2), (.1 ** 2 + .1 ** 2)]))):
-    q = x_attitude[:4]
-    q /= np.linalg.norm(q)                                      # in place, as the reference (:187)
-    omega = x_attitude[4:]
-    q_dot = 0.5 * G(q) @ omega
-    omega_dot = -np.linalg.solve(J, (hat(omega) @ J @ omega))
-    return np.hstack((q_dot, omega_dot))
+def attitude_dynamics(x_attitude, J=np.diag(_J_DEFAULT)):       # :185-196
+    """[q_dot, omega_dot] of a torque-free rigid body: q_dot = 1/2 q (x) (0, omega), J omega_dot = -omega x J omega.
+    Like the reference it normalises the quaternion part of its ARGUMENT in place (:187)."""
+    x_attitude[:4] /= np.linalg.norm(x_attitude[:4])
+    return hm.attitude_rhs(x_attitude, np.asarray(J, dtype=np.float64))
 
 
 def attitude_step(xk, h):                                       # :198-207
-    f1 = attitude_dynamics(xk)
-    f2 = attitude_dynamics(xk + 0.5 * h * f1)
-    f3 = attitude_dynamics(xk + 0.5 * h * f2)
-    f4 = attitude_dynamics(xk + h * f3)
-    xn = xk + (h / 6.0) * (f1 + 2 * f2 + 2 * f3 + f4)
-    xn[:4] /= np.linalg.norm(xn[:4])
-    return xn
+    """One RK4 step + quaternion re-normalisation on the device (`vinsat_attitude_propagate`, one trajectory, one
+    step).  The reference's first stage normalises xk[:4] in place; that side effect is kept."""
+    xk[:4] /= np.linalg.norm(xk[:4])
+    return propagate_attitudes(np.asarray(xk, dtype=np.float64)[None], 1, float(h))[0, 1]
 
 
 def propagate_attitudes(x0, n_steps, h=1.0, stride=1):
