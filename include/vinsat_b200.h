@@ -183,6 +183,18 @@ int vinsat_stream_solve(vinsat_ctx* ctx, const vinsat_stream_desc* desc, int num
                         double lamda_init, int mode, double* states_out, double* seed_states_out,
                         double* window_last_state_out, double* last_hessian_out);
 
+/* ---- Monte-Carlo noise sweeps on a resident batch (configs[3]; the reference's Monte Carlo is the sequential loop of
+ *      od_pipe.py:1063-1086) ------------------------------------------------------------------------------------------
+ * set_truth: the true states [Ttot,10] and noise-free pixels [Mtot,2] the draws are centred on (+ optional true
+ * velocities [Ttot,3] for the velocity error).  perturb: a fresh initial guess as od_pipe.py:962-969 (position +
+ * N(0,pos_sigma), rotation exp(log q + N(0,rot_sigma)), velocity + N(0,vel_sigma)) and fresh pixel noise N(0,sigma_px),
+ * drawn ON THE DEVICE from a counter-based generator keyed by `seed` (same numbers on any GPU).  errors: per problem
+ * max |p - p_true| and max |v - v_true| over its frames, host outputs [P]. */
+int vinsat_batch_mc_set_truth(vinsat_batch* b, const double* states_true, const double* uv_true, const double* vel_true);
+int vinsat_batch_mc_perturb(vinsat_batch* b, uint64_t seed, double sigma_px, double pos_sigma, double rot_sigma,
+                            double vel_sigma);
+int vinsat_batch_mc_errors(vinsat_batch* b, double* pos_err_out, double* vel_err_out);
+
 /* Per-iteration diagnostics of the LAST vinsat_batch_ba_iterate call, for parity tests (host outputs,
  * any may be NULL): r_obs [Mtot,2], weights [Mtot] (after /max and *conf), c_obs [P], D [Ttot,9,9] (without
  * damping), U [Ttot,9,9] (block (i,i+1); last of each problem unused), rhs [Ttot,9], dpose [Ttot,9]. */

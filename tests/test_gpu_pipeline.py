@@ -71,3 +71,40 @@ def test_two_sided_sweep_ragged_lengths(ctx, monkeypatch, lengths, two_sided):
         x = np.linalg.solve(Al, rhs.reshape(-1))
         assert np.allclose(got, x, rtol=1e-4, atol=1e-6 * np.abs(x).max()), (p, T, np.abs(got - x).max())
     assert np.all(np.isfinite(st))
+
+
+def test_device_monte_carlo_draws_and_noise_sweep_pool():
+    """mc_perturb: deterministic per seed, right moments; the pooled noise sweep solves every chunk once and errors grow
+    with sigma_px."""
+    import numpy as np
+    from vinsat_b200 import _lib, synth
+    from vinsat_b200.eval import batch_runner
+    ctx = _lib.Context(0)
+    prs = synth.make_batch(6, 400, 8, seed0=3, sigma_px=0.0)
+    arrays = _lib.concat_problems(prs)
+    st_true = np.concatenate([pr["states_gt"] for pr in prs])
+    b = _lib.Batch(ctx, arrays)
+    b.mc_set_truth(st_true, arrays["landmarks_uv"], np.concatenate([pr["vel_true"] for pr in prs]))
+    b.mc_perturb(7, sigma_px=2.0, pos_sigma=100.0, rot_sigma=0.2, vel_sigma=0.5)
+    s1 = b.get_states()
+    b.eval_resjac()
+    r1, _ = b.fetch_resjac()
+    b.mc_perturb(7, sigma_px=2.0, pos_sigma=100.0, rot_sigma=0.2, vel_sigma=0.5)
+    assert np.array_equal(b.get_states(), s1)                       # same seed, same draw
+    b.mc_perturb(8, sigma_px=2.0, pos_sigma=100.0, rot_sigma=0.2, vel_sigma=0.5)
+    s2 = b.get_states()
+    assert not np.array_equal(s2, s1)
+    dp = (s1[:, :3] - st_true[:, :3]).ravel()
+    dv = (s1[:, 7:] - st_true[:, 7:]).ravel()
+    assert abs(dp.mean()) < 8.0 and 92.0 < dp.std() < 108.0         # N(0, 100 km), 7200 samples
+    assert 0.46 < dv.std() < 0.54
+    assert np.abs(np.linalg.norm(s1[:, 3:7], axis=1) - 1).max() < 1e-12
+    ang = 2 * np.arccos(np.clip(np.abs(np.sum(s1[:, 3:7] * st_true[:, 3:7], axis=1)), 0, 1))
+    assert 0.25 < ang.mean() < 0.40                                 # |N(0, 0.2 I3)| has mean 0.32 rad
+    b.close(); ctx.close()
+    res = batch_runner.run_od_pool(10 * 16, chunk=16, frames=120, obs_per_frame=8, workers=2, pool_key="t")
+    assert sorted(r["chunk"] for r in res) == list(range(10))
+    sw = batch_runner.summarize_noise_sweep(res)
+    assert set(sw) == set(batch_runner.NOISE_SWEEP_PX) and all(v["n"] == 32 for v in sw.values())
+    assert sw[0.25]["pos_m_median"] < sw[4.0]["pos_m_median"]
+    assert sw[0.25]["pos_m_median"] < 500.0

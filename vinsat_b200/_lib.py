@@ -79,6 +79,9 @@ SIGNATURES = {
     "vinsat_batch_last_hessian": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vinsat_stream_solve": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_int, C.c_int, C.c_double, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_batch_mc_set_truth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_batch_mc_perturb": (C.c_int, [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double]),
+    "vinsat_batch_mc_errors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "vinsat_batch_debug_fetch": (C.c_int, [C.c_void_p] + [C.c_void_p] * 7),
     "vinsat_batch_eval_resjac": (C.c_int, [C.c_void_p]),
     "vinsat_batch_fetch_resjac": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -497,6 +500,20 @@ class Batch:
     def od_solve(self, num_iters=20, n_init=10, lamda_init=1e-4, mode=MODE_STEP1S):
         self.ctx.check(self.lib.vinsat_batch_od_solve(self.h, int(num_iters), int(n_init), float(lamda_init),
                                                       int(mode)))
+
+    def mc_set_truth(self, states_true, uv_true, vel_true=None):
+        st, uv = f64(states_true), f64(uv_true)
+        vt = f64(vel_true) if vel_true is not None else None
+        self.ctx.check(self.lib.vinsat_batch_mc_set_truth(self.h, _ptr(st), _ptr(uv), _ptr(vt)))
+
+    def mc_perturb(self, seed, sigma_px=1.0, pos_sigma=100.0, rot_sigma=0.2, vel_sigma=0.44):
+        self.ctx.check(self.lib.vinsat_batch_mc_perturb(self.h, int(seed), float(sigma_px), float(pos_sigma),
+                                                        float(rot_sigma), float(vel_sigma)))
+
+    def mc_errors(self):
+        pe, ve = np.empty(self.P), np.empty(self.P)
+        self.ctx.check(self.lib.vinsat_batch_mc_errors(self.h, _ptr(pe), _ptr(ve)))
+        return pe, ve
 
     def last_hessian(self):
         out = np.empty((self.P, 9, 9))

@@ -48,7 +48,9 @@ void free_all(vinsat_batch* b) {
   if (!b->in_arena)
     for (void* p : ptrs)
       if (p) cudaFree(p);
-  if (b->J) cudaFree(b->J);            // allocated lazily with cudaMalloc, never from the arena
+  if (b->J) cudaFree(b->J);
+  for (void* p : {(void*)b->mc_st_true, (void*)b->mc_uv_true, (void*)b->mc_vel_true, (void*)b->mc_err})
+    if (p) cudaFree(p);            // allocated lazily with cudaMalloc, never from the arena
   for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   b->graphs.clear();
   if (b->h_flags) cudaFreeHost(b->h_flags);

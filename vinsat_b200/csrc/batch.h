@@ -100,6 +100,8 @@ struct vinsat_batch {
   double* la_edge = nullptr;          // [2][10] new states of the first / last owned frame
   double* la_edges_all = nullptr;     // [n_ranks][2][10]
   int32_t* la_chain = nullptr;        // {0, S_total, 0}
+  // ---- Monte-Carlo noise sweeps (mc.cu): true states / pixels the perturbations are drawn around, error scratch ----
+  double *mc_st_true = nullptr, *mc_uv_true = nullptr, *mc_vel_true = nullptr, *mc_err = nullptr;
   bool in_arena = false;       // device buffers come from ctx->arena (never cudaFree'd individually)
   bool have_iter = false;
   bool srec_valid = false;
