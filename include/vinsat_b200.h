@@ -284,6 +284,21 @@ int vinsat_satcam_visibility(vinsat_ctx* ctx, const vinsat_satcam_table* table, 
                              const double* poses, double hfov_deg, int32_t w_px, int32_t h_px, uint8_t* visible_out,
                              int32_t* count_out, double* corner_lonlat_out, int32_t* corner_region_out);
 
+/* ---- (f)2: ingest indexing as integer kernels (od_pipe.py:214-247, 253-288) ------------------------------------------
+ * vinsat_index_detections: `frames` [n_det] = detections[:, 0] (float64 frame ids, sorted non-decreasing as the
+ * reference assumes).  time_idx_out (capacity cap_frames >= #unique frames + n_orbit/1000 + 2) = unique frames with a
+ * knot frame at every multiple of 1000 s between / after the detections (:216-226,242-245), ii_out [n_det] = frame slot
+ * of every detection (:227-228), *n_frames_out (host) = length of time_idx.
+ * vinsat_remove_elems_index: mask [n_det] (1 = keep, the visibility mask of :930), ii / time_idx as above.
+ * frame_keep_out [n_frames] = frames with a surviving observation or knots (:259-263); ii_out = re-indexed surviving
+ * observations, ii - #dropped frames below (:272-282); time_idx_out = time_idx[keep]; counts_out (host) = {#obs kept,
+ * #frames kept}.  Bit-exact against the reference (integers only). */
+int vinsat_index_detections(vinsat_ctx* ctx, int mem, int64_t n_det, const double* frames, int64_t n_orbit,
+                            int64_t cap_frames, int64_t* time_idx_out, int64_t* ii_out, int64_t* n_frames_out);
+int vinsat_remove_elems_index(vinsat_ctx* ctx, int mem, int64_t n_det, int64_t n_frames, const uint8_t* mask,
+                              const int64_t* ii, const int64_t* time_idx, int64_t* ii_out, int64_t* time_idx_out,
+                              uint8_t* frame_keep_out, int64_t* counts_out);
+
 /* ---- measurement helpers ------------------------------------------------------------------ */
 /* FP64 FMA peak of the device (DFMA microbenchmark), TFLOP/s; and a device copy bandwidth, GB/s. */
 int vinsat_measure_fp64_peak(vinsat_ctx* ctx, double* tflops_out);

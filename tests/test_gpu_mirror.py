@@ -87,6 +87,53 @@ def test_propagate_dynamics_init_matches_reference():
 
 
 @pytest.mark.parametrize("name", ["seq_a", "seq_b"])
+def test_ingest_kernels_bit_exact_vs_reference(name):
+    """(f)2: read_detections / remove_elems of the mirror (device kernels for the integer indexing) against the
+    reference's own outputs."""
+    g = load_golden(name)
+    orbit, ld, intr, time_idx, ii = od_pipe.read_detections(False, detections=g["dets"].copy(), orbit_np=g["orbit"].copy())
+    assert np.array_equal(time_idx, g["rd_time_idx"]) and time_idx.dtype == g["rd_time_idx"].dtype
+    assert np.array_equal(ii, g["rd_ii"]) and np.array_equal(orbit, g["rd_orbit"]) and np.array_equal(intr, g["rd_intr"])
+    T = len(time_idx)
+    dummy = torch.zeros((T, 3), dtype=torch.float64)
+    poses = torch.arange(T * 7, dtype=torch.float64).reshape(T, 7)
+    r = od_pipe.remove_elems(torch.tensor(g["vis_mask"]), dummy, dummy, poses, dummy, dummy, None, None, None, None, ii, time_idx)
+    assert np.array_equal(r[9], g["re_ii"]) and np.array_equal(r[10], g["re_time_idx"])
+    assert np.array_equal(r[11].numpy(), g["re_mask"]) and r[2].shape[0] == len(g["re_time_idx"])
+
+
+def test_ingest_kernels_equal_oracle_on_random_and_edge_inputs():
+    import ingest_oracle as io
+    from vinsat_b200 import _lib
+    ctx = _lib.default_context(0)
+    rng = np.random.default_rng(0)
+    cases = [np.array([500.0, 2000.0, 2000.0, 2500.0]),          # a detection ON a knot that was just inserted: duplicate time
+             np.array([1000.0, 2000.0, 3000.0, 3001.0]),         # consecutive detections on knots
+             np.array([7.0]), np.array([0.0, 0.0, 999.0, 1000.0, 1001.0, 5000.0])]
+    for n in (50, 3000, 70000):
+        fr = np.sort(rng.choice(np.arange(0, 12000), size=min(n, 4000) if n < 70000 else 9000, replace=False))
+        cases.append(np.repeat(fr, rng.integers(1, 12, size=len(fr))).astype(np.float64))
+    for frames in cases:
+        for n_orbit in (int(frames[-1]) + 1, 10801, 500):
+            t_o, ii_o = io.index_detections(frames, n_orbit)
+            t_d, ii_d = ctx.index_detections(frames, n_orbit)
+            assert np.array_equal(t_d, t_o) and np.array_equal(ii_d, ii_o), (len(frames), n_orbit)
+            for dens in (0.0, 0.3, 1.0):
+                mask = rng.random(len(frames)) < dens
+                a = io.remove_elems_index(mask, ii_o, t_o)
+                b = ctx.remove_elems_index(mask, ii_o, t_o)
+                assert all(np.array_equal(x, y) for x, y in zip(a, b)), (len(frames), n_orbit, dens)
+    with pytest.raises(_lib.VinsatError, match="sorted"):
+        ctx.index_detections(np.array([5.0, 3.0]), 100)
+    # remove_elems edge cases of the reference's semantics: one survivor / nothing survives (knots stay)
+    time_idx = np.array([3, 8, 1000, 1004, 1010, 2000, 2005]); ii = np.array([0, 0, 1, 3, 3, 4, 6, 6])
+    a = ctx.remove_elems_index(np.array([0, 0, 0, 1, 0, 0, 0, 0], dtype=bool), ii, time_idx)
+    assert list(a[0]) == [1] and list(a[1]) == [1000, 1004, 2000]
+    a = ctx.remove_elems_index(np.zeros(8, dtype=bool), ii, time_idx)
+    assert len(a[0]) == 0 and list(a[1]) == [1000, 2000]
+
+
+@pytest.mark.parametrize("name", ["seq_a", "seq_b"])
 def test_visibility_mask_bit_exact(name):
     g = load_golden(name)
     orbit, ld, intr, time_idx, ii = od_pipe.read_detections(False, detections=g["dets"].copy(), orbit_np=g["orbit"].copy())

@@ -1,10 +1,12 @@
 """Driver-side indexing (a9 of SURVEY.md section 8) against the reference goldens -- integer outputs bit-exact.
-CPU only (host logic of the mirror)."""
+CPU only: the ingest ORACLE (oracle/ingest_oracle.py) and the host geodesy of the mirror.  The product's own indexing
+runs as device kernels and is pinned to the same goldens in tests/test_gpu_mirror.py."""
 import numpy as np
 import pytest
 import torch
 
 from conftest import load_golden
+import ingest_oracle as io
 from vinsat_b200 import od_pipe, trajgen_pipe
 from vinsat_b200 import hostmath as hm
 from vinsat_b200.BA import BA_utils as U
@@ -15,11 +17,16 @@ SEQS = ["seq_a", "seq_b"]
 @pytest.mark.parametrize("name", SEQS)
 def test_read_detections_and_ground_truths(name):
     g = load_golden(name)
-    orbit, ld, intr, time_idx, ii = od_pipe.read_detections(False, detections=g["dets"].copy(), orbit_np=g["orbit"].copy())
+    dets, orbit = g["dets"].copy(), g["orbit"].copy()
+    time_idx, ii = io.index_detections(dets[:, 0], orbit.shape[0])
     assert np.array_equal(time_idx, g["rd_time_idx"]) and time_idx.dtype == g["rd_time_idx"].dtype
     assert np.array_equal(ii, g["rd_ii"])
+    orbit[:, 0], orbit[:, 1], orbit[:, 2] = hm.ecef_to_eci(orbit[:, 0] / 1000, orbit[:, 1] / 1000, orbit[:, 2] / 1000,
+                                                             times=np.arange(orbit.shape[0]))
     assert np.array_equal(orbit, g["rd_orbit"])          # ECEF m -> ECI km, same ops as the reference
+    intr = od_pipe._load_intrinsics()
     assert np.array_equal(intr, g["rd_intr"])
+    ld = {"frame": dets[:, 0], "uv": dets[:, 3:5], "lonlat": dets[:, 1:3], "confidence": dets[:, 5]}
     r = od_pipe.process_ground_truths(orbit, ld, intr, 1.0, time_idx)
     assert np.array_equal(r[2].numpy(), g["pg_poses_gt"])
     assert np.array_equal(r[1].numpy(), g["pg_gt_vel"])
@@ -30,16 +37,10 @@ def test_read_detections_and_ground_truths(name):
 @pytest.mark.parametrize("name", SEQS)
 def test_remove_elems_and_splits(name):
     g = load_golden(name)
-    T = len(g["rd_time_idx"])
-    dummy = torch.zeros((T, 3), dtype=torch.float64)
-    poses = torch.arange(T * 7, dtype=torch.float64).reshape(T, 7)
-    r = od_pipe.remove_elems(torch.tensor(g["vis_mask"]), dummy, dummy, poses, dummy, dummy, None, None, None, None,
-                             g["rd_ii"], g["rd_time_idx"])
-    ii_new, time_idx_new = r[9], r[10]
+    ii_new, time_idx_new, keep = io.remove_elems_index(g["vis_mask"], g["rd_ii"], g["rd_time_idx"])
     assert np.array_equal(ii_new, g["re_ii"])
     assert np.array_equal(time_idx_new, g["re_time_idx"])
-    assert np.array_equal(r[11].numpy(), g["re_mask"])
-    assert r[2].shape[0] == len(g["re_time_idx"])
+    assert keep.sum() == len(g["re_time_idx"])
     splits = []
     i = t = 0
     end = False
@@ -53,14 +54,13 @@ def test_remove_elems_edge_cases():
     # every observation masked out except one; knots survive; frames after the last surviving one stay
     time_idx = np.array([3, 8, 1000, 1004, 1010, 2000, 2005])
     ii = np.array([0, 0, 1, 3, 3, 4, 6, 6])
-    mask = torch.tensor([False, False, False, True, False, False, False, False])
-    z = torch.zeros((7, 3), dtype=torch.float64)
-    r = od_pipe.remove_elems(mask, z, z, z, z, z, None, None, None, None, ii, time_idx)
-    assert list(r[9]) == [1]                          # frames 0,1 dropped below frame 3; knot 1000 kept
-    assert list(r[10]) == [1000, 1004, 2000]
+    mask = np.array([False, False, False, True, False, False, False, False])
+    ii_new, time_idx_new, keep = io.remove_elems_index(mask, ii, time_idx)
+    assert list(ii_new) == [1]                        # frames 0,1 dropped below frame 3; knot 1000 kept
+    assert list(time_idx_new) == [1000, 1004, 2000]
     # empty ragged input: nothing survives
-    r = od_pipe.remove_elems(torch.zeros(8, dtype=torch.bool), z, z, z, z, z, None, None, None, None, ii, time_idx)
-    assert len(r[9]) == 0 and list(r[10]) == [1000, 2000]
+    ii_new, time_idx_new, keep = io.remove_elems_index(np.zeros(8, dtype=bool), ii, time_idx)
+    assert len(ii_new) == 0 and list(time_idx_new) == [1000, 2000]
 
 
 def test_host_helpers_vs_reference_golden():
@@ -141,11 +141,8 @@ def test_window_schedule_reproduces_reference_times(name):
     streaming_version returned: each window contributes [propagated frames but the last] + [last frame]."""
     g = load_golden(name)
     import torch
-    orbit, ld, intr, time_idx, ii = od_pipe.read_detections(False, detections=g["dets"].copy(), orbit_np=g["orbit"].copy())
-    mask = torch.from_numpy(g["vis_mask"])
-    out = od_pipe.remove_elems(mask, *[torch.zeros(len(time_idx), 3)] * 5, torch.zeros(len(ii), 3), torch.zeros(len(ii), 2),
-                               torch.zeros(len(time_idx), 4), torch.zeros(len(time_idx), 3), ii, time_idx)
-    ii2, time_idx2 = out[9], out[10]
+    time_idx, ii = io.index_detections(g["dets"][:, 0], g["orbit"].shape[0])
+    ii2, time_idx2, _ = io.remove_elems_index(g["vis_mask"], ii, time_idx)
     t_final, i_final = od_pipe.window_schedule(ii2, time_idx2)
     assert np.all(np.diff(t_final) > 0) and np.all(np.diff(i_final) >= 0) and i_final[-1] == len(ii2)
     lens = []

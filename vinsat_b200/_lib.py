@@ -102,6 +102,10 @@ SIGNATURES = {
     "vinsat_satcam_table_destroy": (C.c_int, [C.c_void_p]),
     "vinsat_satcam_visibility": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_double,
                                            C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_index_detections": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "vinsat_remove_elems_index": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vinsat_measure_fp64_peak": (C.c_int, [C.c_void_p, c_dp]),
     "vinsat_measure_copy_bw": (C.c_int, [C.c_void_p, C.c_int64, c_dp]),
 }
@@ -281,6 +285,29 @@ class Context:
         self.check(self.lib.vinsat_attitude_propagate(self.h, MEM_HOST, x0.shape[0], int(n_steps), int(stride),
                                                       float(h), _ptr(J), _ptr(x0), _ptr(out)))
         return out
+
+    def index_detections(self, frames, n_orbit):
+        """read_detections' indexing (od_pipe.py:214-247) on the device -> (time_idx with knots, ii)."""
+        fr = f64(frames).reshape(-1)
+        n = fr.shape[0]
+        cap = n + int(n_orbit) // 1000 + 2
+        tix, ii = np.empty(cap, dtype=np.int64), np.empty(n, dtype=np.int64)
+        nf = C.c_int64()
+        self.check(self.lib.vinsat_index_detections(self.h, MEM_HOST, n, _ptr(fr), int(n_orbit), cap, _ptr(tix), _ptr(ii),
+                                                    C.byref(nf)))
+        return tix[:nf.value].copy(), ii
+
+    def remove_elems_index(self, mask, ii, time_idx):
+        """remove_elems' re-indexing (od_pipe.py:253-288) on the device -> (ii_new, time_idx_new, frame keep mask)."""
+        mk = np.ascontiguousarray(mask, dtype=np.uint8).reshape(-1)
+        ii, tix = i64(ii), i64(time_idx)
+        n, T = mk.shape[0], tix.shape[0]
+        ii_out, t_out = np.empty(max(n, 1), dtype=np.int64), np.empty(T, dtype=np.int64)
+        keep = np.empty(T, dtype=np.uint8)
+        cnt = np.zeros(2, dtype=np.int64)
+        self.check(self.lib.vinsat_remove_elems_index(self.h, MEM_HOST, n, T, _ptr(mk), _ptr(ii), _ptr(tix), _ptr(ii_out),
+                                                      _ptr(t_out), _ptr(keep), _ptr(cnt)))
+        return ii_out[:cnt[0]].copy(), t_out[:cnt[1]].copy(), keep.astype(bool)
 
     def stream_solve(self, states, velocities, intrinsics, cum_rot, time_idx, landmarks_xyz, landmarks_uv, confidences,
                      ii, omega, t_final, i_final, num_iters=20, n_init_first=10, lamda_init=1e-4, mode=MODE_STEP1S):

@@ -1,7 +1,7 @@
 """Mirror of ``estimation/od_pipe.py`` (the live OD driver): ``read_detections``, ``process_ground_truths``,
 ``remove_elems``, ``identify_next_batch_new``, ``streaming_version`` keep the reference's names, arguments
-and return values; the BA iterations of each streaming window run on the device (one upload per window,
-20 batched-BA calls, one download).  Citations: path:line under <reference>/estimation.
+and return values.  The integer indexing (unique frames, knots, `ii`, re-indexing after the visibility mask) runs as
+device kernels, the whole window loop of ``streaming_version`` is one device call (``vinsat_stream_solve``).  Citations: path:line under <reference>/estimation.
 
 The debug drivers of the reference (``od_pipe`` [stale], ``full_batch_optimization``, ``*_debugging``)
 stop in ``ipdb.set_trace()`` and are out of scope.
@@ -40,29 +40,12 @@ def read_detections(sample_dets=False, detections=None, orbit_np=None, orbit_fil
     landmarks = detections if detections is not None else np.load(detections_file_name, allow_pickle=True)
     landmarks_dict = {"frame": landmarks[:, 0], "uv": landmarks[:, 3:5], "lonlat": landmarks[:, 1:3],
                       "confidence": landmarks[:, 5]}
-    uniq, counts = np.unique(landmarks[:, 0], return_counts=True)
-    time_idx = uniq.astype(np.int64)
-    filler_idx = time_idx.min() // 1000 + 1
-    filler_offset = 0
-    time_idx_new, slots = [], []
-    for i, tidx in enumerate(time_idx):                     # :218-228
-        if tidx == filler_idx * 1000:
-            filler_idx += 1
-        while tidx > filler_idx * 1000:
-            time_idx_new.append(filler_idx * 1000)
-            filler_idx += 1
-            filler_offset += 1
-        time_idx_new.append(tidx)
-        slots.append(i + filler_offset)
-    ii = np.repeat(np.array(slots, dtype=np.int64), counts)
     orbit = orbit_np if orbit_np is not None else np.load(orbit_file_name, allow_pickle=True)
+    # :214-228,242-247 -- unique frames, knot insertion and the obs -> frame slot map as integer kernels on the device
+    time_idx_new, ii = _ctx().index_detections(landmarks[:, 0], orbit.shape[0])
     orbit[:, 0], orbit[:, 1], orbit[:, 2] = hm.ecef_to_eci(orbit[:, 0] / 1000, orbit[:, 1] / 1000, orbit[:, 2] / 1000,
                                                              times=np.arange(orbit.shape[0]))     # :240
-    if time_idx[-1] < orbit.shape[0]:                        # :242-245
-        while filler_idx * 1000 < (orbit.shape[0] // 1000) * 1000 + 1:
-            time_idx_new.append(filler_idx * 1000)
-            filler_idx += 1
-    return orbit, landmarks_dict, _load_intrinsics(), np.array(time_idx_new), ii
+    return orbit, landmarks_dict, _load_intrinsics(), time_idx_new, ii
 
 
 def process_ground_truths(orbit, landmarks_dict, intrinsics, dt, time_idx):
@@ -84,20 +67,13 @@ def process_ground_truths(orbit, landmarks_dict, intrinsics, dt, time_idx):
 
 def remove_elems(mask, gt_pos_eci, gt_vel_eci, poses_gt_eci, gt_quat_eci, gt_quat_eci_full, landmarks_xyz,
                  landmarks_uv, intrinsics, gt_acceleration, ii, time_idx):
-    """od_pipe.py:253-288 as an exclusive prefix sum over the kept-frame mask: frames kept =
-    frames with a surviving observation or knots; ii_new[k] = ii_old[k] - #{dropped frames < ii_old[k]}."""
+    """od_pipe.py:253-288: frames kept = frames with a surviving observation or knots; surviving observations are
+    re-indexed by an exclusive prefix sum over the dropped frames -- device kernels
+    (`vinsat_remove_elems_index`: mark, scan, compact)."""
     mask_np = mask.numpy() if isinstance(mask, torch.Tensor) else np.asarray(mask)
-    ii_old = ii[mask_np]
-    keep = np.zeros(time_idx.shape[0], dtype=bool)
-    keep[np.unique(ii_old)] = True
-    keep |= (time_idx % 1000 == 0)
-    dropped = ~keep
-    if len(ii_old):
-        dropped[int(ii_old.max()) + 1:] = False           # the reference only walks i <= ii_old.max() (:272)
-    shift = np.concatenate([[0], np.cumsum(dropped)[:-1]])  # dropped frames strictly below each index
-    ii_new = ii_old - shift[ii_old]
+    ii_new, time_idx_new, keep = _ctx().remove_elems_index(mask_np, ii, time_idx)
     return (gt_pos_eci[keep], gt_vel_eci, poses_gt_eci[keep], gt_quat_eci[keep], gt_quat_eci_full, landmarks_xyz,
-            landmarks_uv, intrinsics, gt_acceleration, ii_new, time_idx[keep], mask)
+            landmarks_uv, intrinsics, gt_acceleration, ii_new, time_idx_new, mask)
 
 
 def identify_next_batch_new(ii, time_idx, i, t):
