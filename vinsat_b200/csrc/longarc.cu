@@ -33,10 +33,14 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // partial sums over the OWNED frames (one warp, fixed order => deterministic)
 //   which=0: sums[0] = sum grec[f][27] (|r_obs| unweighted), sums[1] = sum_{owned pairs} |r_pred| (7 components)
 //   which=1: sums[0] = sum e_obs[f],                         sums[1] = sum_{owned pairs} e_dyn[f]
+// The linearisation's sums go to sums[0..1], the trial's to sums[2..3] (the weighted observation sum already divided
+// by the GLOBAL largest weight, which the all-reduce(MAX) after ASSEMBLE left in wmax), so that ONE all-reduce of the
+// four doubles and ONE host read at the end of a trial carry everything the accept test needs.
 __global__ void __launch_bounds__(32) k_la_sums(int64_t lo, int64_t hi, int which, int initialize,
                                                 const int32_t* __restrict__ gap, const double* __restrict__ grec,
                                                 const double* __restrict__ drec, const double* __restrict__ e_obs,
-                                                const double* __restrict__ e_dyn, double* __restrict__ sums) {
+                                                const double* __restrict__ e_dyn,
+                                                const unsigned long long* __restrict__ wmax, double* __restrict__ sums) {
   const int lane = threadIdx.x;
   double so = 0.0, sd = 0.0;
   for (int64_t f = lo + lane; f < hi; f += 32) {
@@ -54,7 +58,15 @@ __global__ void __launch_bounds__(32) k_la_sums(int64_t lo, int64_t hi, int whic
   }
   so = warp_sum_d(so);
   sd = warp_sum_d(sd);
-  if (lane == 0) { sums[0] = so; sums[1] = sd; sums[2] = 0.0; sums[3] = 0.0; }
+  if (lane == 0) {
+    if (which == 0) { sums[0] = so; sums[1] = sd; sums[2] = 0.0; sums[3] = 0.0; }
+    else {
+      const unsigned long long wb = wmax[0];
+      const double w = __longlong_as_double((long long)wb);
+      sums[2] = (wb && w > 0.0) ? so / w : 0.0;
+      sums[3] = sd;
+    }
+  }
 }
 
 __global__ void k_la_set_lam(double lam_v, double* __restrict__ lam, int32_t* __restrict__ active) {
@@ -167,7 +179,7 @@ int vinsat_la_stage(vinsat_batch* b, int stage, int64_t i0, int64_t i1, double d
       return launch_system_build(b, (int)i0, d0, vc);                             // i0 = initialize, d0 = Sigma
     case VINSAT_LA_SUMS_INIT:
       VS_LAUNCH(ctx, F_ACCEPT, k_la_sums, 1, 32, 0, b->own_lo, b->own_hi, 0, (int)i0, b->gap, b->grec, b->drec, b->e_obs,
-                b->e_dyn, b->la_sums);
+                b->e_dyn, b->wmax, b->la_sums);
       return VINSAT_OK;
     case VINSAT_LA_SET_LAM:
       VS_LAUNCH(ctx, F_ACCEPT, k_la_set_lam, 1, 1, 0, d0, b->lam, b->active);
@@ -202,8 +214,9 @@ int vinsat_la_stage(vinsat_batch* b, int stage, int64_t i0, int64_t i1, double d
                                 (int)i0, b->e_dyn, nullptr));
       return VINSAT_OK;
     case VINSAT_LA_SUMS_TRIAL:
+      if (i1) VS_CUDA(ctx, cudaMemsetAsync(b->la_sums, 0, 2 * sizeof(double), ctx->stream));   // i1: drop the (already reduced) init sums
       VS_LAUNCH(ctx, F_ACCEPT, k_la_sums, 1, 32, 0, b->own_lo, b->own_hi, 1, (int)i0, b->gap, b->grec, b->drec, b->e_obs,
-                b->e_dyn, b->la_sums);
+                b->e_dyn, b->wmax, b->la_sums);
       return VINSAT_OK;
     case VINSAT_LA_COMMIT:
       std::swap(b->st, b->st_new);

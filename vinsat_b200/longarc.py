@@ -225,11 +225,9 @@ class LongArc:
         if not initialize:
             self._stage(DYNAMICS, self.mode)
             self._stage(SYSTEM, 0, 0, Sigma)
-        self._stage(SUMS_INIT, init)
-        so, sd = self._global_sums()
+        self._stage(SUMS_INIT, init)                      # local sums -> BUF_SUMS[0:2]; reduced together with the trial's
         n = 2.0 * self.M + (6.0 if initialize else 7.0) * max(self.T - 1, 0)
-        init_res = (so + sq * sd) / n
-        wmax = float(self._read(BUF_WMAX).view(np.float64)[0])
+        init_res = None
         lam = float(lamda_init)
         ntrials = 0
         while True:
@@ -245,9 +243,15 @@ class LongArc:
             self._stage(RETRACT)
             self._exchange_ghosts(current=False)
             self._stage(TRIAL, self.mode, init)
-            self._stage(SUMS_TRIAL, init)
-            so1, sd1 = self._global_sums()
-            residual = ((so1 / wmax if wmax > 0 else 0.0) + sq * sd1) / n
+            # trial sums -> BUF_SUMS[2:4] (observation part already divided by the global max weight on the device);
+            # from the second trial on the already-reduced init sums are zeroed first
+            self._stage(SUMS_TRIAL, init, 1 if ntrials > 0 else 0)
+            self._all_reduce(BUF_SUMS, "sum")
+            self._after_collective()
+            s4 = self._read(BUF_SUMS)                     # the ONE host read of the trial
+            if init_res is None:
+                init_res = (float(s4[0]) + sq * float(s4[1])) / n
+            residual = (float(s4[2]) + sq * float(s4[3])) / n
             ntrials += 1
             lam = lam * 10
             if residual < init_res or lam > 1e4:
