@@ -612,6 +612,448 @@ __global__ void __launch_bounds__(32, 9) k_obs_assemble_2pass(int64_t T, int64_t
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent, double-buffered variant of the two-pass kernel (default).  ncu on the two-pass kernel (r01/r02): 13.7 %
+// of the warp slots, FP64 pipe 27 % busy, a CTA lives ~25 k cycles of which ~4 k are FP64 issue: the rest is the
+// exposed latency of a CTA that first learns its observation range, then waits for its tile, then for the frame
+// constants.  Here one warp per scheduler stays resident (4 one-warp CTAs per SM, 51 KB of shared memory each) and
+// walks tiles of 32 frames: while tile i is processed the observation tile AND the frame rows (states, intrinsics,
+// CSR offsets, problem ids) of tile i+1 arrive by cp.async, and the observation range of tile i+2 is already being
+// read.  Math and accumulation order are those of the two-pass kernel (bit-identical records).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPaSlotBytes = k2pChunk * 8;
+constexpr int kPaInBytes = 7 * kPaSlotBytes + k2pChunk * 4;                // 7 double slots + frame ids
+constexpr int kPaFinBytes = 32 * 10 * 8 + 32 * 4 * 8 + 40 * 4 + 32 * 4;    // states | intrinsics | obs_start[33] (padded) | fprob
+constexpr int kPaSmemBytes = 2 * kPaInBytes + 2 * kPaFinBytes + 32 * k2pFrameRec * 8;
+
+__global__ void __launch_bounds__(32, 4) k_obs_assemble_pers(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
+                                                             const int32_t* __restrict__ oframe,
+                                                             const int32_t* __restrict__ fprob,
+                                                             const double* __restrict__ X, const double* __restrict__ uv,
+                                                             const double* __restrict__ conf,
+                                                             const double* __restrict__ st,
+                                                             const double* __restrict__ intr,
+                                                             const double* __restrict__ c_obs, WeightParams wp,
+                                                             double* __restrict__ wu_out, double* __restrict__ grec,
+                                                             unsigned long long* __restrict__ wmax,
+                                                             const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;
+  extern __shared__ __align__(16) unsigned char smp[];
+  const int lane = threadIdx.x;
+  const int64_t n_tiles = (T + 31) / 32;
+  auto in_tile = [&](int b) { return reinterpret_cast<double*>(smp + b * kPaInBytes); };
+  auto in_ofr = [&](int b) { return reinterpret_cast<int32_t*>(smp + b * kPaInBytes + 7 * kPaSlotBytes); };
+  auto fin_st = [&](int b) { return reinterpret_cast<double*>(smp + 2 * kPaInBytes + b * kPaFinBytes); };
+  auto fin_intr = [&](int b) { return fin_st(b) + 320; };
+  auto fin_os = [&](int b) { return reinterpret_cast<int32_t*>(fin_intr(b) + 128); };
+  auto fin_fp = [&](int b) { return fin_os(b) + 40; };
+  double* fdat = reinterpret_cast<double*>(smp + 2 * kPaInBytes + 2 * kPaFinBytes);
+
+  auto issue_obs = [&](double* tile, int32_t* ofr, int base, int n) {
+    for (int i = lane; i < n; i += 32) {
+      const int k = base + i;
+      __pipeline_memcpy_async(&tile[i], &X[k], 8);
+      __pipeline_memcpy_async(&tile[k2pChunk + i], &X[M + k], 8);
+      __pipeline_memcpy_async(&tile[2 * k2pChunk + i], &X[2 * M + k], 8);
+      __pipeline_memcpy_async(&tile[3 * k2pChunk + i], &uv[k], 8);
+      __pipeline_memcpy_async(&tile[4 * k2pChunk + i], &uv[M + k], 8);
+      __pipeline_memcpy_async(&tile[5 * k2pChunk + i], &conf[k], 8);
+      __pipeline_memcpy_async(&ofr[i], &oframe[k], 4);
+    }
+  };
+  // frame rows of a tile: 32 x 80 B of states and 32 x 32 B of intrinsics are contiguous -> 16-byte copies
+  auto issue_frames = [&](int b, int64_t f0) {
+    const int nf = (int)min((int64_t)32, T - f0);
+    const double* s0 = st + f0 * 10;
+    const double* i0 = intr + f0 * 4;
+    for (int i = lane; i < nf * 5; i += 32) __pipeline_memcpy_async(fin_st(b) + 2 * i, s0 + 2 * i, 16);
+    for (int i = lane; i < nf * 2; i += 32) __pipeline_memcpy_async(fin_intr(b) + 2 * i, i0 + 2 * i, 16);
+    for (int i = lane; i < nf + 1; i += 32) __pipeline_memcpy_async(fin_os(b) + i, obs_start + f0 + i, 4);
+    if (lane < nf) __pipeline_memcpy_async(fin_fp(b) + lane, fprob + f0 + lane, 4);
+  };
+  auto tile_range = [&](int64_t tile, int& kb, int& ke) {
+    const int64_t f0 = tile * 32;
+    kb = obs_start[f0];
+    ke = obs_start[min(f0 + 32, T)];
+  };
+
+  int64_t tile = blockIdx.x;
+  if (tile >= n_tiles) return;
+  int kb, ke, kb_n = 0, ke_n = 0;
+  tile_range(tile, kb, ke);
+  issue_frames(0, tile * 32);
+  issue_obs(in_tile(0), in_ofr(0), kb, min(k2pChunk, ke - kb));
+  __pipeline_commit();
+  int64_t tile_n = tile + gridDim.x;
+  if (tile_n < n_tiles) tile_range(tile_n, kb_n, ke_n);
+  const double inv_am2 = wp.alpha_is_two ? 0.0 : 1.0 / wp.am2;
+  int buf = 0;
+  for (; tile < n_tiles; tile = tile_n, tile_n += gridDim.x, buf ^= 1) {
+    const int64_t f0 = tile * 32;
+    const int64_t f = f0 + lane;
+    const bool valid = f < T;
+    // prefetch the next tile (its range was read one iteration ago) and start reading the range of the one after it
+    const bool has_next = tile_n < n_tiles;
+    int kb_nn = 0, ke_nn = 0;
+    if (has_next) {
+      issue_frames(buf ^ 1, tile_n * 32);
+      issue_obs(in_tile(buf ^ 1), in_ofr(buf ^ 1), kb_n, min(k2pChunk, ke_n - kb_n));
+    }
+    __pipeline_commit();
+    if (tile_n + gridDim.x < n_tiles) tile_range(tile_n + gridDim.x, kb_nn, ke_nn);
+    __pipeline_wait_prior(1);
+    __syncwarp();
+    double* tilep = in_tile(buf);
+    int32_t* ofr = in_ofr(buf);
+    int k0 = 0, k1 = 0, p = 0;
+    double Rt[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) Rt[i] = 0.0;
+    double4 ci = make_double4(0, 0, 0, 0);
+    {
+      double* fd = fdat + lane * k2pFrameRec;
+      double px = 0, py = 0, pz = 0;
+      FrameWeight fw = {1.0, 1.0, 1.0};
+      if (valid) {
+        k0 = fin_os(buf)[lane]; k1 = fin_os(buf)[lane + 1];
+        p = fin_fp(buf)[lane];
+        if (k1 > k0) {
+          const double c = c_obs[p];                      // L2-resident, issued before the rotation arithmetic
+          const double* s = fin_st(buf) + lane * 10;
+          ci = *reinterpret_cast<const double4*>(fin_intr(buf) + lane * 4);
+          px = s[0]; py = s[1]; pz = s[2];
+          const double qn = 1.0 / sqrt(s[3] * s[3] + s[4] * s[4] + s[5] * s[5] + s[6] * s[6]);
+          const double x = s[3] * qn, y = s[4] * qn, z = s[5] * qn, w = s[6] * qn;
+          Rt[0] = 1 - 2 * (y * y + z * z); Rt[1] = 2 * (x * y + z * w);     Rt[2] = 2 * (x * z - y * w);
+          Rt[3] = 2 * (x * y - z * w);     Rt[4] = 1 - 2 * (x * x + z * z); Rt[5] = 2 * (y * z + x * w);
+          Rt[6] = 2 * (x * z + y * w);     Rt[7] = 2 * (y * z - x * w);     Rt[8] = 1 - 2 * (x * x + y * y);
+          fw = frame_weight(c, wp);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 9; i++) fd[i] = Rt[i];
+      fd[9] = px; fd[10] = py; fd[11] = pz;
+      fd[12] = ci.x; fd[13] = ci.y; fd[14] = ci.z; fd[15] = ci.w;
+      fd[16] = fw.inv_c; fd[17] = fw.inv_c2;
+    }
+    const int p_first = __shfl_sync(0xffffffffu, p, 0);
+    const bool one_problem = __all_sync(0xffffffffu, !valid || p == p_first);
+    double sN[5] = {0, 0, 0, 0, 0}, sNH[9], sHNH[6] = {0, 0, 0, 0, 0, 0}, sm[3] = {0, 0, 0}, sHm[3] = {0, 0, 0}, sabs = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) sNH[i] = 0.0;
+    double wloc = 0.0;
+    __syncwarp();
+    for (int base = kb; base < ke; base += k2pChunk) {
+      const int n = min(k2pChunk, ke - base);
+      if (base > kb) {
+        // a tile with more than one chunk of observations (dense frames): the extra chunks are not prefetched
+        issue_obs(tilep, ofr, base, n);
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
+        __syncwarp();
+      }
+      // ---- pass 1: one lane per observation (independent iterations: five chains in flight per lane)
+#pragma unroll 5
+      for (int i = lane; i < n; i += 32) {
+        const int lf = ofr[i] - (int)f0;
+        const double* fd = fdat + lf * k2pFrameRec;
+        const double dx = tilep[i] - fd[9], dy = tilep[k2pChunk + i] - fd[10], dz = tilep[2 * k2pChunk + i] - fd[11];
+        const double Xc = fd[0] * dx + fd[1] * dy + fd[2] * dz;
+        const double Yc = fd[3] * dx + fd[4] * dy + fd[5] * dz;
+        const double Zc = fd[6] * dx + fd[7] * dy + fd[8] * dz;
+        const double d = 1.0 / fmax(Zc, 0.1);
+        const double a = fd[12] * d, bb = fd[13] * d;
+        const double ru = tilep[3 * k2pChunk + i] - (a * Xc + fd[14]), rv = tilep[4 * k2pChunk + i] - (bb * Yc + fd[15]);
+        FrameWeight fw; fw.inv_c = fd[16]; fw.inv_am2 = inv_am2; fw.inv_c2 = fd[17];
+        const double wraw = 0.5 * (robust_component_fast(ru, fw, wp) + robust_component_fast(rv, fw, wp));
+        const double w = wraw * tilep[5 * k2pChunk + i];
+        tilep[i] = Xc; tilep[k2pChunk + i] = Yc; tilep[2 * k2pChunk + i] = Zc;
+        tilep[3 * k2pChunk + i] = ru; tilep[4 * k2pChunk + i] = rv;
+        tilep[5 * k2pChunk + i] = w;
+        tilep[6 * k2pChunk + i] = d;
+        if (one_problem) wloc = fmax(wloc, wraw);
+        else if (wraw > 0.0) atomicMax(&wmax[fin_fp(buf)[lf]], (unsigned long long)__double_as_longlong(wraw));
+      }
+      __syncwarp();
+      // ---- pass 2: one lane per frame
+      const int lo = max(k0, base), hi = min(k1, base + n);
+      for (int k = lo; k < hi; k++) {
+        const int i = k - base;
+        const double Xc = tilep[i], Yc = tilep[k2pChunk + i], Zc = tilep[2 * k2pChunk + i];
+        const double ru = tilep[3 * k2pChunk + i], rv = tilep[4 * k2pChunk + i];
+        const double w = tilep[5 * k2pChunk + i], d = tilep[6 * k2pChunk + i];
+        const double live = (Zc >= 0.1) ? 1.0 : 0.0;
+        const double a = ci.x * d, bb = ci.y * d;
+        const double cc = -a * Xc * d * live, ee = -bb * Yc * d * live;
+        sabs += fabs(ru) + fabs(rv);
+        const double wa = w * a, wb = w * bb;
+        const double n00 = wa * a, n02 = wa * cc, n11 = wb * bb, n12 = wb * ee, n22 = w * (cc * cc + ee * ee);
+        sN[0] += n00; sN[1] += n02; sN[2] += n11; sN[3] += n12; sN[4] += n22;
+        const double h00 = -n02 * Yc, h01 = n02 * Xc - n00 * Zc, h02 = n00 * Yc;
+        const double h10 = n11 * Zc - n12 * Yc, h11 = n12 * Xc, h12 = -n11 * Xc;
+        const double h20 = n12 * Zc - n22 * Yc, h21 = n22 * Xc - n02 * Zc, h22 = n02 * Yc - n12 * Xc;
+        sNH[0] += h00; sNH[1] += h01; sNH[2] += h02; sNH[3] += h10; sNH[4] += h11; sNH[5] += h12;
+        sNH[6] += h20; sNH[7] += h21; sNH[8] += h22;
+        sHNH[0] += Zc * h10 - Yc * h20; sHNH[1] += Zc * h11 - Yc * h21; sHNH[2] += Zc * h12 - Yc * h22;
+        sHNH[3] += Xc * h21 - Zc * h01; sHNH[4] += Xc * h22 - Zc * h02; sHNH[5] += Yc * h02 - Xc * h12;
+        const double m0 = wa * ru, m1 = wb * rv, m2 = w * (cc * ru + ee * rv);
+        sm[0] += m0; sm[1] += m1; sm[2] += m2;
+        sHm[0] += Zc * m1 - Yc * m2; sHm[1] += Xc * m2 - Zc * m0; sHm[2] += Yc * m0 - Xc * m1;
+      }
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) wu_out[base + i] = tilep[5 * k2pChunk + i];
+      __syncwarp();
+    }
+    if (one_problem) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wloc = fmax(wloc, __shfl_xor_sync(0xffffffffu, wloc, o));
+      if (lane == 0 && wloc > 0.0) atomicMax(&wmax[p_first], (unsigned long long)__double_as_longlong(wloc));
+    }
+    if (valid) {
+      const double N[9] = {sN[0], 0.0, sN[1], 0.0, sN[2], sN[3], sN[1], sN[3], sN[4]};
+      double NR[9];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) NR[i * 3 + j] = N[i * 3] * Rt[j] + N[i * 3 + 1] * Rt[3 + j] + N[i * 3 + 2] * Rt[6 + j];
+      double out[VS_GREC];
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int bcol = a; bcol < 3; bcol++)
+          out[idx++] = Rt[a] * NR[bcol] + Rt[3 + a] * NR[3 + bcol] + Rt[6 + a] * NR[6 + bcol];
+#pragma unroll
+        for (int bcol = 0; bcol < 3; bcol++)
+          out[idx++] = -2.0 * (Rt[a] * sNH[bcol] + Rt[3 + a] * sNH[3 + bcol] + Rt[6 + a] * sNH[6 + bcol]);
+      }
+      out[idx++] = 4.0 * sHNH[0]; out[idx++] = 4.0 * sHNH[1]; out[idx++] = 4.0 * sHNH[2];
+      out[idx++] = 4.0 * sHNH[3]; out[idx++] = 4.0 * sHNH[4];
+      out[idx++] = 4.0 * sHNH[5];
+#pragma unroll
+      for (int a = 0; a < 3; a++) out[21 + a] = -(Rt[a] * sm[0] + Rt[3 + a] * sm[1] + Rt[6 + a] * sm[2]);
+#pragma unroll
+      for (int a = 0; a < 3; a++) out[24 + a] = 2.0 * sHm[a];
+      out[27] = sabs;
+      double* g = grec + f * VS_GREC;
+#pragma unroll
+      for (int i = 0; i < VS_GREC; i += 2) *reinterpret_cast<double2*>(g + i) = make_double2(out[i], out[i + 1]);
+    }
+    __syncwarp();       // fdat and the consumed buffers are rewritten by the next iteration
+    kb = kb_n; ke = ke_n;
+    kb_n = kb_nn; ke_n = ke_nn;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Half-tile variant: ONE WARP OWNS 16 FRAMES, two lanes per frame.  Measurements that led here (B200, 1024 x 1000 x 10):
+// the 32-frame two-pass kernel runs 9 warps per SM (24 KB of shared memory and 158 registers per warp) at 0.31 ms; the
+// persistent double-buffered version of it -- every load prefetched one tile ahead, 4 warps per SM -- takes 0.49 ms.
+// So the kernel is not waiting for memory: a lone warp issues one instruction per ~5 cycles (FP64 dependent-issue
+// latency 8.25 cycles, issue interval 2.3, measured by tools/ubench/fp64_lat.cu) and only more resident warps fill the
+// pipe.  Halving the tile halves the shared memory per warp (12 KB), the two lanes of a frame take its even / odd
+// observations (5 instead of 10 sequential accumulation steps) and are combined by one xor-shuffle per sum.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kHtFrames = 16;
+constexpr int kHtChunk = 160;                 // observations per chunk (16 frames x 10; more obs => more chunks)
+constexpr int kHtSmemBytes = (k2pSlots * kHtChunk + kHtFrames * k2pFrameRec) * 8 + kHtChunk * 4;
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(32, kMinBlocks) k_obs_assemble_half(int64_t T, int64_t M,
+                                                                      const int32_t* __restrict__ obs_start,
+                                                                      const int32_t* __restrict__ oframe,
+                                                                      const int32_t* __restrict__ fprob,
+                                                                      const double* __restrict__ X,
+                                                                      const double* __restrict__ uv,
+                                                                      const double* __restrict__ conf,
+                                                                      const double* __restrict__ st,
+                                                                      const double* __restrict__ intr,
+                                                                      const double* __restrict__ c_obs, WeightParams wp,
+                                                                      double* __restrict__ wu_out, double* __restrict__ grec,
+                                                                      unsigned long long* __restrict__ wmax,
+                                                                      const int32_t* __restrict__ gate) {
+  if (gate && *gate) return;
+  extern __shared__ __align__(16) double smh[];
+  double* tile = smh;                                                   // [k2pSlots][kHtChunk]
+  double* fdat = smh + k2pSlots * kHtChunk;                             // [16][k2pFrameRec]
+  int32_t* ofr = reinterpret_cast<int32_t*>(fdat + kHtFrames * k2pFrameRec);
+  const int lane = threadIdx.x;
+  const int half = lane & 1;                  // which observations of the frame this lane accumulates
+  const int lfr = lane >> 1;                  // local frame of the lane pair
+  const int64_t f0 = (int64_t)blockIdx.x * kHtFrames;
+  const int64_t f = f0 + lfr;
+  const bool valid = f < T;
+  const int kb = obs_start[f0];
+  const int ke = obs_start[min(f0 + kHtFrames, T)];
+  auto issue_chunk = [&](int base) {
+    const int n = min(kHtChunk, ke - base);
+    for (int i = lane; i < n; i += 32) {
+      const int k = base + i;
+      __pipeline_memcpy_async(&tile[i], &X[k], 8);
+      __pipeline_memcpy_async(&tile[kHtChunk + i], &X[M + k], 8);
+      __pipeline_memcpy_async(&tile[2 * kHtChunk + i], &X[2 * M + k], 8);
+      __pipeline_memcpy_async(&tile[3 * kHtChunk + i], &uv[k], 8);
+      __pipeline_memcpy_async(&tile[4 * kHtChunk + i], &uv[M + k], 8);
+      __pipeline_memcpy_async(&tile[5 * kHtChunk + i], &conf[k], 8);
+      __pipeline_memcpy_async(&ofr[i], &oframe[k], 4);
+    }
+    __pipeline_commit();
+  };
+  issue_chunk(kb);
+  int k0 = 0, k1 = 0, p = 0;
+  double cix = 0.0, ciy = 0.0;
+  {
+    // frame constants: computed by the even lane of the pair, shared through fdat
+    double* fd = fdat + lfr * k2pFrameRec;
+    if (valid) {
+      k0 = obs_start[f]; k1 = obs_start[f + 1];
+      p = fprob[f];
+    }
+    if (half == 0) {
+      double Rt[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rt[i] = 0.0;
+      double4 ci = make_double4(0, 0, 0, 0);
+      double px = 0, py = 0, pz = 0;
+      FrameWeight fw = {1.0, 1.0, 1.0};
+      if (valid && k1 > k0) {
+        fw = frame_weight(c_obs[p], wp);
+        const double* s = st + f * 10;
+        ci = *reinterpret_cast<const double4*>(intr + f * 4);
+        px = s[0]; py = s[1]; pz = s[2];
+        const double qn = 1.0 / sqrt(s[3] * s[3] + s[4] * s[4] + s[5] * s[5] + s[6] * s[6]);
+        const double x = s[3] * qn, y = s[4] * qn, z = s[5] * qn, w = s[6] * qn;
+        Rt[0] = 1 - 2 * (y * y + z * z); Rt[1] = 2 * (x * y + z * w);     Rt[2] = 2 * (x * z - y * w);
+        Rt[3] = 2 * (x * y - z * w);     Rt[4] = 1 - 2 * (x * x + z * z); Rt[5] = 2 * (y * z + x * w);
+        Rt[6] = 2 * (x * z + y * w);     Rt[7] = 2 * (y * z - x * w);     Rt[8] = 1 - 2 * (x * x + y * y);
+      }
+#pragma unroll
+      for (int i = 0; i < 9; i++) fd[i] = Rt[i];
+      fd[9] = px; fd[10] = py; fd[11] = pz;
+      fd[12] = ci.x; fd[13] = ci.y; fd[14] = ci.z; fd[15] = ci.w;
+      fd[16] = fw.inv_c; fd[17] = fw.inv_c2;
+    }
+    __syncwarp();
+    cix = fd[12]; ciy = fd[13];
+  }
+  const int p_first = __shfl_sync(0xffffffffu, p, 0);
+  const bool one_problem = __all_sync(0xffffffffu, !valid || p == p_first);
+  const double inv_am2 = wp.alpha_is_two ? 0.0 : 1.0 / wp.am2;
+  double sN[5] = {0, 0, 0, 0, 0}, sNH[9], sHNH[6] = {0, 0, 0, 0, 0, 0}, sm[3] = {0, 0, 0}, sHm[3] = {0, 0, 0}, sabs = 0.0;
+#pragma unroll
+  for (int i = 0; i < 9; i++) sNH[i] = 0.0;
+  double wloc = 0.0;
+  for (int base = kb; base < ke; base += kHtChunk) {
+    const int n = min(kHtChunk, ke - base);
+    __pipeline_wait_prior(0);
+    __syncwarp();
+    // ---- pass 1: one lane per observation
+#pragma unroll 5
+    for (int i = lane; i < n; i += 32) {
+      const int lf = ofr[i] - (int)f0;
+      const double* fd = fdat + lf * k2pFrameRec;
+      const double dx = tile[i] - fd[9], dy = tile[kHtChunk + i] - fd[10], dz = tile[2 * kHtChunk + i] - fd[11];
+      const double Xc = fd[0] * dx + fd[1] * dy + fd[2] * dz;
+      const double Yc = fd[3] * dx + fd[4] * dy + fd[5] * dz;
+      const double Zc = fd[6] * dx + fd[7] * dy + fd[8] * dz;
+      const double d = 1.0 / fmax(Zc, 0.1);
+      const double a = fd[12] * d, bb = fd[13] * d;
+      const double ru = tile[3 * kHtChunk + i] - (a * Xc + fd[14]), rv = tile[4 * kHtChunk + i] - (bb * Yc + fd[15]);
+      FrameWeight fw; fw.inv_c = fd[16]; fw.inv_am2 = inv_am2; fw.inv_c2 = fd[17];
+      const double wraw = 0.5 * (robust_component_fast(ru, fw, wp) + robust_component_fast(rv, fw, wp));
+      const double w = wraw * tile[5 * kHtChunk + i];
+      tile[i] = Xc; tile[kHtChunk + i] = Yc; tile[2 * kHtChunk + i] = Zc;
+      tile[3 * kHtChunk + i] = ru; tile[4 * kHtChunk + i] = rv;
+      tile[5 * kHtChunk + i] = w;
+      tile[6 * kHtChunk + i] = d;
+      if (one_problem) wloc = fmax(wloc, wraw);
+      else if (wraw > 0.0) atomicMax(&wmax[fprob[f0 + lf]], (unsigned long long)__double_as_longlong(wraw));
+    }
+    __syncwarp();
+    // ---- pass 2: two lanes per frame, even / odd observations of the frame (fixed split => deterministic sums)
+    const int lo = max(k0, base), hi = min(k1, base + n);
+    for (int k = lo + ((half + 2 - ((lo - k0) & 1)) & 1); k < hi; k += 2) {     // k - k0 has the parity of `half`
+      const int i = k - base;
+      const double Xc = tile[i], Yc = tile[kHtChunk + i], Zc = tile[2 * kHtChunk + i];
+      const double ru = tile[3 * kHtChunk + i], rv = tile[4 * kHtChunk + i];
+      const double w = tile[5 * kHtChunk + i], d = tile[6 * kHtChunk + i];
+      const double live = (Zc >= 0.1) ? 1.0 : 0.0;
+      const double a = cix * d, bb = ciy * d;
+      const double cc = -a * Xc * d * live, ee = -bb * Yc * d * live;
+      sabs += fabs(ru) + fabs(rv);
+      const double wa = w * a, wb = w * bb;
+      const double n00 = wa * a, n02 = wa * cc, n11 = wb * bb, n12 = wb * ee, n22 = w * (cc * cc + ee * ee);
+      sN[0] += n00; sN[1] += n02; sN[2] += n11; sN[3] += n12; sN[4] += n22;
+      const double h00 = -n02 * Yc, h01 = n02 * Xc - n00 * Zc, h02 = n00 * Yc;
+      const double h10 = n11 * Zc - n12 * Yc, h11 = n12 * Xc, h12 = -n11 * Xc;
+      const double h20 = n12 * Zc - n22 * Yc, h21 = n22 * Xc - n02 * Zc, h22 = n02 * Yc - n12 * Xc;
+      sNH[0] += h00; sNH[1] += h01; sNH[2] += h02; sNH[3] += h10; sNH[4] += h11; sNH[5] += h12;
+      sNH[6] += h20; sNH[7] += h21; sNH[8] += h22;
+      sHNH[0] += Zc * h10 - Yc * h20; sHNH[1] += Zc * h11 - Yc * h21; sHNH[2] += Zc * h12 - Yc * h22;
+      sHNH[3] += Xc * h21 - Zc * h01; sHNH[4] += Xc * h22 - Zc * h02; sHNH[5] += Yc * h02 - Xc * h12;
+      const double m0 = wa * ru, m1 = wb * rv, m2 = w * (cc * ru + ee * rv);
+      sm[0] += m0; sm[1] += m1; sm[2] += m2;
+      sHm[0] += Zc * m1 - Yc * m2; sHm[1] += Xc * m2 - Zc * m0; sHm[2] += Yc * m0 - Xc * m1;
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) wu_out[base + i] = tile[5 * kHtChunk + i];
+    __syncwarp();
+    if (base + kHtChunk < ke) issue_chunk(base + kHtChunk);
+  }
+  if (one_problem) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wloc = fmax(wloc, __shfl_xor_sync(0xffffffffu, wloc, o));
+    if (lane == 0 && wloc > 0.0) atomicMax(&wmax[p_first], (unsigned long long)__double_as_longlong(wloc));
+  }
+  // combine the two halves of every frame (even + odd, always in this order)
+  auto pair_sum = [&](double v) {
+    const double o = __shfl_xor_sync(0xffffffffu, v, 1);
+    return half == 0 ? v + o : o + v;
+  };
+#pragma unroll
+  for (int i = 0; i < 5; i++) sN[i] = pair_sum(sN[i]);
+#pragma unroll
+  for (int i = 0; i < 9; i++) sNH[i] = pair_sum(sNH[i]);
+#pragma unroll
+  for (int i = 0; i < 6; i++) sHNH[i] = pair_sum(sHNH[i]);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { sm[i] = pair_sum(sm[i]); sHm[i] = pair_sum(sHm[i]); }
+  sabs = pair_sum(sabs);
+  if (valid) {
+    // the rotation back to the world frame is split between the two lanes: even lane rows 0..13, odd lane rows 14..27
+    const double* Rt = fdat + lfr * k2pFrameRec;
+    const double N[9] = {sN[0], 0.0, sN[1], 0.0, sN[2], sN[3], sN[1], sN[3], sN[4]};
+    double NR[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) NR[i * 3 + j] = N[i * 3] * Rt[j] + N[i * 3 + 1] * Rt[3 + j] + N[i * 3 + 2] * Rt[6 + j];
+    double out[VS_GREC];
+    int idx = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+      for (int bcol = a; bcol < 3; bcol++)
+        out[idx++] = Rt[a] * NR[bcol] + Rt[3 + a] * NR[3 + bcol] + Rt[6 + a] * NR[6 + bcol];
+#pragma unroll
+      for (int bcol = 0; bcol < 3; bcol++)
+        out[idx++] = -2.0 * (Rt[a] * sNH[bcol] + Rt[3 + a] * sNH[3 + bcol] + Rt[6 + a] * sNH[6 + bcol]);
+    }
+    out[idx++] = 4.0 * sHNH[0]; out[idx++] = 4.0 * sHNH[1]; out[idx++] = 4.0 * sHNH[2];
+    out[idx++] = 4.0 * sHNH[3]; out[idx++] = 4.0 * sHNH[4];
+    out[idx++] = 4.0 * sHNH[5];
+#pragma unroll
+    for (int a = 0; a < 3; a++) out[21 + a] = -(Rt[a] * sm[0] + Rt[3 + a] * sm[1] + Rt[6 + a] * sm[2]);
+#pragma unroll
+    for (int a = 0; a < 3; a++) out[24 + a] = 2.0 * sHm[a];
+    out[27] = sabs;
+    double* g = grec + f * VS_GREC;
+#pragma unroll
+    for (int i = 0; i < VS_GREC; i += 2)
+      if ((i < 14) == (half == 0)) *reinterpret_cast<double2*>(g + i) = make_double2(out[i], out[i + 1]);
+  }
+}
+
 int launch_obs_assemble(vinsat_batch* b, double alpha) {
   vinsat_ctx* ctx = b->ctx;
   WeightParams wp;
@@ -634,6 +1076,27 @@ int launch_obs_assemble(vinsat_batch* b, double alpha) {
               b->obs_start, b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax);
     return VINSAT_OK;
   }
+  if (variant == 0 || variant == 16 || variant == 12) {      // half-tile kernel (default)
+    const int grid = (int)ceil_div(b->T, kHtFrames);
+    if (variant == 12) {
+      VS_SMEM_OPTIN(ctx, SM_SPARE1, k_obs_assemble_half<12>, kHtSmemBytes);
+      VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_half<12>, grid, 32, kHtSmemBytes, b->T, b->M, b->obs_start, b->oframe,
+                b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax, b->gate_arg);
+    } else {
+      VS_SMEM_OPTIN(ctx, SM_SPARE2, k_obs_assemble_half<16>, kHtSmemBytes);
+      VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_half<16>, grid, 32, kHtSmemBytes, b->T, b->M, b->obs_start, b->oframe,
+                b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax, b->gate_arg);
+    }
+    return VINSAT_OK;
+  }
+  if (variant == 4) {             // persistent double-buffered kernel (kept for the record: slower, see above)
+    const int64_t n_tiles = ceil_div(b->T, 32);
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)ctx->sm_count * 4);
+    VS_SMEM_OPTIN(ctx, SM_SPARE0, k_obs_assemble_pers, kPaSmemBytes);
+    VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_pers, grid, 32, kPaSmemBytes, b->T, b->M, b->obs_start, b->oframe,
+              b->fprob, b->X, b->uv, b->conf, b->st, b->intr, b->c_obs, wp, b->wu, b->grec, b->wmax, b->gate_arg);
+    return VINSAT_OK;
+  }
   const int smem = (k2pSlots * k2pChunk + 32 * k2pFrameRec) * (int)sizeof(double) + k2pChunk * (int)sizeof(int32_t);
   VS_SMEM_OPTIN(ctx, SM_ASM_2PASS, k_obs_assemble_2pass, smem);
   VS_LAUNCH(ctx, F_OBS_ASSEMBLE, k_obs_assemble_2pass, ceil_div(b->T, 32), 32, smem, b->T, b->M, b->obs_start, b->oframe,
@@ -642,6 +1105,7 @@ int launch_obs_assemble(vinsat_batch* b, double alpha) {
 }
 
 // trial residual, observation part: e_obs[f] = sum_k wu_k (|ru| + |rv|) at st_new (BA_filtering.py:61,66)
+constexpr int kTrialUnroll = 5;
 template <int kGroup>
 __global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const int32_t* __restrict__ obs_start,
                                                    const int32_t* __restrict__ fprob,
@@ -663,13 +1127,28 @@ __global__ void __launch_bounds__(256) k_obs_trial(int64_t T, int64_t M, const i
       const double* s = st + f * 10;
       const double4 ci = *reinterpret_cast<const double4*>(intr + f * 4);
       const Quat q = {s[3], s[4], s[5], s[6]};
-      for (int k = k0 + gl; k < k1; k += kGroup) {
-        ProjOut o = project_exact(s[0], s[1], s[2], q, X[k], X[M + k], X[2 * M + k], ci.x, ci.y, ci.z, ci.w);
-        const double w = wu[k];
-        const double ru = xsub(uv[k], o.u), rv = xsub(uv[M + k], o.v);
-        r_next[k] = ru;
-        r_next[M + k] = rv;
-        e += fabs(ru * w) + fabs(rv * w);
+      // kTrialUnroll observations per pass with ALL their loads issued before the first use: the kernel is bound by
+      // memory latency (ncu r01: long_scoreboard 20 of 24 stall cycles per issue at 36 % occupancy), so the loads in
+      // flight per thread are what sets its bandwidth.  Out-of-range slots re-read the last observation and are masked.
+      for (int kb = k0 + gl; kb < k1; kb += kGroup * kTrialUnroll) {
+        double x[kTrialUnroll], y[kTrialUnroll], z[kTrialUnroll], mu[kTrialUnroll], mv[kTrialUnroll], w[kTrialUnroll];
+#pragma unroll
+        for (int j = 0; j < kTrialUnroll; j++) {
+          const int k = min(kb + j * kGroup, k1 - 1);
+          x[j] = X[k]; y[j] = X[M + k]; z[j] = X[2 * M + k];
+          mu[j] = uv[k]; mv[j] = uv[M + k]; w[j] = wu[k];
+        }
+#pragma unroll
+        for (int j = 0; j < kTrialUnroll; j++) {
+          const int k = kb + j * kGroup;
+          if (k < k1) {
+            ProjOut o = project_exact(s[0], s[1], s[2], q, x[j], y[j], z[j], ci.x, ci.y, ci.z, ci.w);
+            const double ru = xsub(mu[j], o.u), rv = xsub(mv[j], o.v);
+            r_next[k] = ru;
+            r_next[M + k] = rv;
+            e += fabs(ru * w[j]) + fabs(rv * w[j]);
+          }
+        }
       }
     }
   }

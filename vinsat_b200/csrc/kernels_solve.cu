@@ -112,27 +112,34 @@ __global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const in
     return;
   }
   unsigned long long* cand = sel_keys + n;
-  // all copies of the problem's residuals are in flight at once (cp.async, no register round trip)
-  for (int i = tid; i < n; i += kSelThreads) {
-    const int comp = i >= Mp ? 1 : 0;
-    __pipeline_memcpy_async(&sel_keys[i], &r[(int64_t)comp * M + k0 + (i - comp * Mp)], 8);
-  }
-  __pipeline_commit();
+  // keys = bit patterns of |r|, loaded straight into registers (eight independent loads in flight per thread), made
+  // non-negative and parked in shared memory.  Bits that are identical in every key carry no information: the same
+  // pass ORs (key ^ key0) so that the 11-bit digits can start at the highest differing bit.
   if (tid == 0) s_diff = 0ull;
-  __pipeline_wait_prior(0);
-  __syncthreads();
-  // keys = bit patterns of |r|.  Bits that are identical in every key carry no information: find the highest
-  // differing bit with a block-wide OR of (key ^ key0) and start the 11-bit digits THERE.
   {
-    const unsigned long long key0 = sel_keys[0] & 0x7fffffffffffffffull;
+    const unsigned long long* r0 = reinterpret_cast<const unsigned long long*>(r) + k0;          // u residuals
+    const unsigned long long* r1 = reinterpret_cast<const unsigned long long*>(r) + M + k0;      // v residuals
+    const unsigned long long key0 = r0[0] & 0x7fffffffffffffffull;
     unsigned long long d = 0ull;
-    for (int i = tid; i < n; i += kSelThreads) {
-      const unsigned long long key = sel_keys[i] & 0x7fffffffffffffffull;
-      sel_keys[i] = key;
-      d |= key ^ key0;
+    constexpr int kLd = 8;
+    for (int base = tid; base < n; base += kSelThreads * kLd) {
+      unsigned long long k[kLd];
+#pragma unroll
+      for (int j = 0; j < kLd; j++) {
+        const int i = base + j * kSelThreads;
+        k[j] = i < n ? (i < Mp ? r0[i] : r1[i - Mp]) : key0;
+      }
+#pragma unroll
+      for (int j = 0; j < kLd; j++) {
+        const int i = base + j * kSelThreads;
+        const unsigned long long key = k[j] & 0x7fffffffffffffffull;
+        if (i < n) sel_keys[i] = key;
+        d |= key ^ key0;
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d |= __shfl_xor_sync(0xffffffffu, d, o);
+    __syncthreads();                       // s_diff = 0 is visible
     if (lane == 0 && d) atomicOr(&s_diff, d);
   }
   __syncthreads();
@@ -195,9 +202,21 @@ __global__ void __launch_bounds__(kSelThreads) k_select_smem(int64_t M, const in
         if ((key >> shift) == (npre >> shift)) cand[atomicAdd(&s_cnt, 1u)] = key;
       }
       __syncthreads();
-      list = cand;
-      nlist = (int)bc;
-      all_match = true;
+      // The selected bin holds a few dozen keys: finish by COUNTING instead of four more digit passes (each of which
+      // costs six block-wide barriers): candidate t is the answer iff exactly `rank` candidates order before it
+      // (ties broken by position, so equal keys get distinct ranks).
+      const unsigned int rk2 = (unsigned int)s_rank;
+      for (unsigned int t = tid; t < bc; t += kSelThreads) {
+        const unsigned long long mine = cand[t];
+        unsigned int below = 0;
+        for (unsigned int j = 0; j < bc; j++) {
+          const unsigned long long o = cand[j];
+          below += (o < mine || (o == mine && j < t)) ? 1u : 0u;
+        }
+        if (below == rk2) s_prefix = mine;
+      }
+      __syncthreads();
+      break;
     } else {
       all_match = false;
     }
