@@ -183,6 +183,28 @@ int vinsat_stream_solve(vinsat_ctx* ctx, const vinsat_stream_desc* desc, int num
                         double lamda_init, int mode, double* states_out, double* seed_states_out,
                         double* window_last_state_out, double* last_hessian_out);
 
+/* ---- (f)4: the prior-regularised variant (BA_reg, BA/BA_filtering.py:100-210) ------------------------------------------
+ * vinsat_prior = prior_gpu (BA/BA_utils.py:604-676): states / prop_states [N,10], hessian_state [N,6,6] (position /
+ * velocity information, row-major), hessian_rot [N,3,3].  r_out [N,7] = [H e ; quat_coeff (1 - |.|)].  Block outputs
+ * (all three or none): Jp_out [N,6,9] = the diagonal blocks of the reference's dense Jacobian (everything off the block
+ * diagonal is exactly zero there), Hqp_out [N,9,9], qgrad_out [N,9].  NOTE the parameter order (vel_coeff before
+ * quat_coeff) is prior_gpu's own; BA_reg passes its quat / vel coefficients the other way round (:122) -- the mirror
+ * keeps that call as it is.
+ * vinsat_propagate_chain_cov = propagate_dynamics_cov_init (BA/BA_utils.py:222-248): state0 [10], vel0 [3], hessian
+ * [9,9] (last_hessian of the previous window), omega [(tdiff+duration),3] -> states_out [(duration+1),10],
+ * hessian_state_out [(duration+1),6,6], hessian_rot_out [(duration+1),3,3].
+ * vinsat_batch_set_prior + vinsat_batch_ba_reg_iterate: one BA_reg() call per problem of the batch (initialize=False, the
+ * only way the reference calls it, od_pipe.py:893), same lamda_io / ntrials_out contract as vinsat_batch_ba_iterate. */
+int vinsat_prior(vinsat_ctx* ctx, int mem, int64_t n_frames, const double* states, const double* prop_states,
+                 double vel_coeff, double quat_coeff, const double* hessian_state, const double* hessian_rot,
+                 double* r_out, double* Jp_out, double* Hqp_out, double* qgrad_out);
+int vinsat_propagate_chain_cov(vinsat_ctx* ctx, int mem, int64_t tdiff, int64_t duration, double dt, const double* state0,
+                               const double* vel0, const double* hessian, const double* omega, double* states_out,
+                               double* hessian_state_out, double* hessian_rot_out);
+int vinsat_batch_set_prior(vinsat_batch* b, int mem, const double* states_prior, const double* hessian_state,
+                           const double* hessian_rot);
+int vinsat_batch_ba_reg_iterate(vinsat_batch* b, int iter, int mode, double* lamda_io, int32_t* ntrials_out);
+
 /* ---- Monte-Carlo noise sweeps on a resident batch (configs[3]; the reference's Monte Carlo is the sequential loop of
  *      od_pipe.py:1063-1086) ------------------------------------------------------------------------------------------
  * set_truth: the true states [Ttot,10] and noise-free pixels [Mtot,2] the draws are centred on (+ optional true

@@ -121,3 +121,42 @@ def test_lower_median_and_weights_corner():
     assert c == 1.0 and np.all(w == 1.0)
     w, c = o.robust_weights(r, np.ones(2), 3)
     assert np.isfinite(w).all() and w.max() == 1.0
+
+
+# ------------------------------------------------------------------------------------------------ (f)4
+def test_reg_prior_vs_reference():
+    import reg_oracle as ro
+    g = load_golden("ba_reg")
+    r, Jp, Hqp, qg = ro.prior(g["pri_states"], g["pri_prop"], 1, 1, g["pri_Hs"], g["pri_Hr"])
+    assert rel(r, g["pri_r"]) < 1e-12
+    assert rel(Jp, g["pri_Jp"]) < 1e-12
+    scale = np.abs(np.einsum("nki,nkj->nij", g["pri_Jp"], g["pri_Jp"])).max()
+    assert np.abs(Hqp - g["pri_Hqp"]).max() < 1e-12 * scale          # rounding-noise terms (~1e-15 |H_rot|), see the oracle
+    assert np.abs(qg - g["pri_qgrad"]).max() < 1e-12 * np.abs(g["pri_r"]).max()
+    assert rel(ro.prior(g["pri_states"], g["pri_prop"], 1, 100, g["pri_Hs"], g["pri_Hr"], jacobian=False), g["pri_r_trial"]) < 1e-12
+
+
+def test_reg_covariance_propagation_vs_reference():
+    import reg_oracle as ro
+    g = load_golden("ba_reg")
+    s_t, v_t, hs, hr = ro.propagate_dynamics_cov_init(g["cov_state"], g["cov_vel"], g["cov_hessian"], g["cov_omega"],
+                                                      int(g["cov_tdiff"]), int(g["cov_duration"]))
+    assert rel(s_t, g["cov_states_t"]) < 1e-12 and rel(v_t, g["cov_vel_t"]) < 1e-12
+    assert rel(hs, g["cov_hess_state_t"]) < 1e-9 and rel(hr, g["cov_hess_rot_t"]) < 1e-9
+
+
+def test_reg_ba_reg_iterates_track_reference():
+    import reg_oracle as ro
+    g = load_golden("ba_reg")
+    pr = {k[7:]: v for k, v in g.items() if k.startswith("reg_in_")}
+    st, lam = g["reg_start"].copy(), 1e-4
+    for j in range(len(g["reg_lamda_hist"])):
+        it = int(g["reg_first_iter"]) + j
+        st, lam, H, info = ro.ba_reg_iteration(it, st, g["reg_prior"], g["reg_Hs"], g["reg_Hr"], pr["cum_rot"], pr["uv"],
+                                               pr["xyz"], pr["ii"], pr["time_idx"], pr["intr"], pr["conf"], lam)
+        ref = g["reg_states_hist"][j]
+        assert np.abs(st[:, :3] - ref[:, :3]).max() < 1e-3, j          # 1 m
+        assert np.abs(st[:, 7:] - ref[:, 7:]).max() < 1e-6, j          # 1 mm/s
+        assert np.abs(st[:, 3:7] - ref[:, 3:7]).max() < 1e-7, j
+        assert lam == g["reg_lamda_hist"][j], j
+        assert rel(H, g["reg_hessian_hist"][j]) < 1e-6, j

@@ -79,3 +79,44 @@ def BA(iter, states, velocities, imu_meas, landmarks, landmarks_xyz, ii, time_id
         d = np.abs(states_new[0, :, :3].numpy() - gt[:, :3]).mean(axis=0)
         print("final pos: ", torch.from_numpy(d), float(np.linalg.norm(d)))
     return states_new, velocities, float(lam[0]), last_hessian
+
+
+
+def BA_reg(iter, states, velocities, states_prior, velocity_prior, hessian_state_t, hessian_rot_t, imu_meas, landmarks,
+           landmarks_xyz, ii, time_idx, intrinsics, confidences, Sigma, V, lamda_init, poses_gt_eci, initialize=False,
+           use_reg=True):
+    """The prior-regularised iteration (BA_filtering.py:100-210): BA() plus the prior terms of `prior_gpu` around
+    `states_prior` with the information matrices `hessian_state_t` (1,T,6,6) / `hessian_rot_t` (1,T,3,3).  Same return
+    tuple as BA().  Only initialize=False exists on the device -- it is the only way the reference calls it
+    (od_pipe.py:893); `velocity_prior` and `use_reg` are unused by the reference as well."""
+    if initialize:
+        raise NotImplementedError("BA_reg(initialize=True) is never used by the reference (od_pipe.py:893)")
+    st = _np(states)
+    assert st.shape[0] == 1, "the reference is batch-size-1 only (SURVEY 0.11)"
+    T = st.shape[1]
+    ii_np = np.asarray(ii, dtype=np.int64).reshape(-1)
+    M = len(ii_np)
+    uv = _np(landmarks).reshape(M, 2)
+    xyz = _np(landmarks_xyz).reshape(M, 3)
+    conf = _np(confidences).reshape(M)
+    if M > 1 and np.any(np.diff(ii_np) < 0):
+        order = np.argsort(ii_np, kind="stable")
+        ii_np, uv, xyz, conf = ii_np[order], uv[order], xyz[order], conf[order]
+    arrays = dict(frame_off=np.array([0, T], dtype=np.int64), obs_off=np.array([0, M], dtype=np.int64),
+                  states=np.ascontiguousarray(st[0]), intrinsics=np.ascontiguousarray(_np(intrinsics).reshape(T, 4)),
+                  cum_rot=np.ascontiguousarray(_cum_rot_of(imu_meas)),
+                  time_idx=np.ascontiguousarray(time_idx, dtype=np.int64), landmarks_xyz=np.ascontiguousarray(xyz),
+                  landmarks_uv=np.ascontiguousarray(uv), confidences=np.ascontiguousarray(conf),
+                  ii=np.ascontiguousarray(ii_np))
+    ent, resident = _batch_for(arrays, (landmarks, landmarks_xyz, confidences, ii, time_idx, intrinsics, imu_meas))
+    b = ent["batch"]
+    b.set_prior(_np(states_prior)[0], _np(hessian_state_t)[0], _np(hessian_rot_t)[0])
+    lam, ntr = b.ba_reg_iterate(int(iter), float(lamda_init), mode=config.mode())
+    new = b.get_states()
+    ent["last"] = new.copy()
+    states_new = torch.from_numpy(new)[None]
+    last_hessian = torch.from_numpy(b.last_hessian())
+    gt = _np(poses_gt_eci)
+    d = np.abs(states_new[0, :, :3].numpy() - gt[:, :3]).mean(axis=0)
+    print("final pos: ", torch.from_numpy(d), float(np.linalg.norm(d)))          # :194
+    return states_new, velocities, float(lam[0]), last_hessian

@@ -188,3 +188,41 @@ geodetic_to_ecef = hm.geodetic_to_ecef
 convert_latlong_to_cartesian = hm.convert_latlong_to_cartesian
 convert_pos_to_quaternion = hm.convert_pos_to_quaternion
 deg_to_rad = np.deg2rad
+
+
+# ---- (f)4: prior-regularised variant ---------------------------------------------------------------------------------
+def prior_gpu(states, prop_states, vel_coeff, quat_coeff, hessian_state_t, hessian_rot_t, jacobian=True, initialize=False):
+    """BA_utils.py:604-676.  states / prop_states (1,N,10), hessian_state_t (1,N,6,6), hessian_rot_t (1,N,3,3).
+    Returns res (1,N,7) [, Jp (1,6N,9N), Hqp (1,9N,9N), qgrad (1,N,9)] like the reference: the dense matrices are built
+    from the device's diagonal blocks (the reference's are exactly zero elsewhere).  initialize=True returns the
+    reference's zero tensors (:611-614)."""
+    st = _np(states)
+    assert st.shape[0] == 1, "the reference is batch-size-1 only (SURVEY 0.11)"
+    N = st.shape[1]
+    if initialize:
+        if jacobian:
+            return (torch.zeros((1, N, 6)), torch.zeros((1, N * 6, N * 9)), torch.zeros((1, N * 9, N * 9)),
+                    torch.zeros((1, N, 9)))
+        return torch.zeros((1, N, 6))
+    out = _ctx().prior(st[0], _np(prop_states)[0], vel_coeff, quat_coeff, _np(hessian_state_t)[0], _np(hessian_rot_t)[0],
+                       jacobian=jacobian)
+    if not jacobian:
+        return torch.from_numpy(out)[None]
+    r, Jp, Hqp, qg = out
+    Jd = np.zeros((N, 6, N, 9))
+    Hd = np.zeros((N, 9, N, 9))
+    idx = np.arange(N)
+    Jd[idx, :, idx, :] = Jp
+    Hd[idx, :, idx, :] = Hqp
+    return (torch.from_numpy(r)[None], torch.from_numpy(Jd.reshape(1, N * 6, N * 9)),
+            torch.from_numpy(Hd.reshape(1, N * 9, N * 9)), torch.from_numpy(qg)[None])
+
+
+def propagate_dynamics_cov_init(states, velocities, hessian, omega, tdiff, duration, dt):
+    """BA_utils.py:222-248: states (1,10), velocities (1,3), hessian (1,9,9), omega (1,tdiff+duration,3) ->
+    (states_t (1,duration+1,10), velocities_t (1,duration+1,3), hessian_state_t (1,duration+1,6,6),
+    hessian_rot_t (1,duration+1,3,3)); one device call (orbit + attitude chains with their covariances)."""
+    st, hs, hr = _ctx().propagate_chain_cov(_np(states)[0], _np(velocities)[0], _np(hessian).reshape(-1, 9, 9)[0],
+                                            _np(omega)[0], int(tdiff), int(duration), float(dt))
+    t = torch.from_numpy
+    return t(st)[None], t(np.ascontiguousarray(st[:, 7:]))[None], t(hs)[None], t(hr)[None]

@@ -79,6 +79,12 @@ SIGNATURES = {
     "vinsat_batch_last_hessian": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vinsat_stream_solve": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_int, C.c_int, C.c_double, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_prior": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_propagate_chain_cov": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_batch_set_prior": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vinsat_batch_ba_reg_iterate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "vinsat_batch_mc_set_truth": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vinsat_batch_mc_perturb": (C.c_int, [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double]),
     "vinsat_batch_mc_errors": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -309,6 +315,29 @@ class Context:
                                                       _ptr(t_out), _ptr(keep), _ptr(cnt)))
         return ii_out[:cnt[0]].copy(), t_out[:cnt[1]].copy(), keep.astype(bool)
 
+    def prior(self, states, prop_states, vel_coeff, quat_coeff, hessian_state, hessian_rot, jacobian=True):
+        """prior_gpu (BA_utils.py:604-676) in block-diagonal form: r (N,7) [, Jp (N,6,9), Hqp (N,9,9), qgrad (N,9)]."""
+        st, pr = f64(states).reshape(-1, 10), f64(prop_states).reshape(-1, 10)
+        N = st.shape[0]
+        hs, hr = f64(hessian_state).reshape(N, 6, 6), f64(hessian_rot).reshape(N, 3, 3)
+        r = np.empty((N, 7))
+        Jp = np.empty((N, 6, 9)) if jacobian else None
+        Hqp = np.empty((N, 9, 9)) if jacobian else None
+        qg = np.empty((N, 9)) if jacobian else None
+        self.check(self.lib.vinsat_prior(self.h, MEM_HOST, N, _ptr(st), _ptr(pr), float(vel_coeff), float(quat_coeff),
+                                         _ptr(hs), _ptr(hr), _ptr(r), _ptr(Jp), _ptr(Hqp), _ptr(qg)))
+        return (r, Jp, Hqp, qg) if jacobian else r
+
+    def propagate_chain_cov(self, state0, vel0, hessian, omega, tdiff, duration, dt=1.0):
+        """propagate_dynamics_cov_init (BA_utils.py:222-248): -> states_t (duration+1,10), Hs_t (duration+1,6,6),
+        Hr_t (duration+1,3,3)."""
+        s0, v0, hh = f64(state0).reshape(10), f64(vel0).reshape(3), f64(hessian).reshape(9, 9)
+        om = f64(omega).reshape(-1, 3)
+        st = np.empty((duration + 1, 10)); hs = np.empty((duration + 1, 6, 6)); hr = np.empty((duration + 1, 3, 3))
+        self.check(self.lib.vinsat_propagate_chain_cov(self.h, MEM_HOST, int(tdiff), int(duration), float(dt), _ptr(s0),
+                                                       _ptr(v0), _ptr(hh), _ptr(om), _ptr(st), _ptr(hs), _ptr(hr)))
+        return st, hs, hr
+
     def stream_solve(self, states, velocities, intrinsics, cum_rot, time_idx, landmarks_xyz, landmarks_uv, confidences,
                      ii, omega, t_final, i_final, num_iters=20, n_init_first=10, lamda_init=1e-4, mode=MODE_STEP1S):
         """streaming_version's window loop (od_pipe.py:987-1060) in one device call; see include/vinsat_b200.h.
@@ -527,6 +556,17 @@ class Batch:
     def od_solve(self, num_iters=20, n_init=10, lamda_init=1e-4, mode=MODE_STEP1S):
         self.ctx.check(self.lib.vinsat_batch_od_solve(self.h, int(num_iters), int(n_init), float(lamda_init),
                                                       int(mode)))
+
+    def set_prior(self, states_prior, hessian_state, hessian_rot):
+        sp = f64(states_prior).reshape(self.T, 10)
+        hs, hr = f64(hessian_state).reshape(self.T, 6, 6), f64(hessian_rot).reshape(self.T, 3, 3)
+        self.ctx.check(self.lib.vinsat_batch_set_prior(self.h, MEM_HOST, _ptr(sp), _ptr(hs), _ptr(hr)))
+
+    def ba_reg_iterate(self, it, lamda, mode=MODE_STEP1S):
+        lam = np.ascontiguousarray(np.broadcast_to(np.asarray(lamda, dtype=np.float64), (self.P,))).copy()
+        ntr = np.zeros(self.P, dtype=np.int32)
+        self.ctx.check(self.lib.vinsat_batch_ba_reg_iterate(self.h, int(it), int(mode), _ptr(lam), _ptr(ntr)))
+        return lam, ntr
 
     def mc_set_truth(self, states_true, uv_true, vel_true=None):
         st, uv = f64(states_true), f64(uv_true)

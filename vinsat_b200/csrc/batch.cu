@@ -49,7 +49,8 @@ void free_all(vinsat_batch* b) {
     for (void* p : ptrs)
       if (p) cudaFree(p);
   if (b->J) cudaFree(b->J);
-  for (void* p : {(void*)b->mc_st_true, (void*)b->mc_uv_true, (void*)b->mc_vel_true, (void*)b->mc_err})
+  for (void* p : {(void*)b->mc_st_true, (void*)b->mc_uv_true, (void*)b->mc_vel_true, (void*)b->mc_err, (void*)b->pr_st,
+                  (void*)b->pr_Hs, (void*)b->pr_Hr, (void*)b->e_pr_init, (void*)b->e_pr})
     if (p) cudaFree(p);            // allocated lazily with cudaMalloc, never from the arena
   for (auto& kv : b->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   b->graphs.clear();
@@ -398,14 +399,18 @@ static int wait_flag(vinsat_batch* b) {
 static int issue_trial(vinsat_batch* b, int initialize, int mode, double Sigma, double quat_coeff, double vel_coeff,
                        int32_t* h_dst = nullptr) {
   vinsat_ctx* ctx = b->ctx;
+  const bool reg = b->reg_iter;
   VS_TRY(launch_solve_retract(b, initialize));
   VS_TRY(launch_obs_trial(b));
+  // BA_reg evaluates the trial's dynamics residual with quat_coeff_prior = 1 and its prior with (vel, quat) coefficients
+  // (1, 100) (BA_filtering.py:169-170): reproduced as is
   if (!initialize)
     VS_TRY(launch_dyn_trial(ctx, b->n_pairs, b->dyn_order, b->st_new, b->crot, b->gap, b->active, b->fprob,
-                            quat_coeff, vel_coeff, mode, b->e_dyn, nullptr, b->gate_arg));
+                            reg ? 1.0 : quat_coeff, vel_coeff, mode, b->e_dyn, nullptr, b->gate_arg));
+  if (reg) VS_TRY(launch_prior_trial(b, 1.0, vel_coeff));
   if (b->gate_arg) VS_TRY(launch_gated_zero(b, nullptr, 0, b->flags, 1));
   else VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, sizeof(int32_t), ctx->stream));
-  VS_TRY(launch_accept(b, initialize, Sigma));
+  VS_TRY(launch_accept(b, initialize, Sigma, reg ? b->e_pr : nullptr));
   if (b->gate_arg) VS_TRY(launch_gate_publish(b));
   VS_CUDA(ctx, cudaMemcpyAsync(h_dst ? h_dst : b->h_flags, b->flags, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   return VINSAT_OK;
@@ -432,7 +437,8 @@ static int issue_iteration_head(vinsat_batch* b, int iter, int initialize, int m
   // The plain (unpartitioned) sweep builds its columns on the fly from the per-frame records (fused system
   // build); the partitioned sweep and the diagnostics read the materialised records.
   if (!initialize && !b->fused_system) VS_TRY(launch_system_build(b, 0, Sigma, vel_coeff));
-  VS_TRY(launch_init_residual(b, initialize, Sigma, 0.0, lam_dev_in));
+  if (b->reg_iter) VS_TRY(launch_prior_linearize(b, 1.0, 1.0));      // prior_gpu(.., quat_coeff_prior = 1, vel_coeff_prior = 1, ..) (:122)
+  VS_TRY(launch_init_residual(b, initialize, Sigma, 0.0, lam_dev_in, b->reg_iter ? b->e_pr_init : nullptr));
   return issue_trial(b, initialize, mode, Sigma, quat_coeff, vel_coeff, h_dst);
 }
 
@@ -447,7 +453,7 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
   const bool have_residuals = b->r_valid;
   if (have_residuals) std::swap(b->r, b->r_next);
   static const bool no_fuse = getenv("VINSAT_NO_FUSED_SYSTEM") != nullptr || getenv("VINSAT_ONE_SIDED_SWEEP") != nullptr;
-  b->fused_system = !initialize && !b->partitioned && !no_fuse;
+  b->fused_system = !initialize && !b->partitioned && !no_fuse && !b->reg_iter;      // BA_reg adds its blocks to the records
   b->srec_valid = !initialize && !b->fused_system;
   b->last_sigma = Sigma;
   b->cur_sigma = Sigma;
@@ -462,7 +468,7 @@ static int ba_iterate_device(vinsat_batch* b, int iter, int initialize, int mode
   // Measured on B200: P = 64 x T = 1000 gains 24 % from the replay (launch bound), P = 1024 LOSES 5 % (20 distinct
   // graphs of long kernels: the per-graph launch cost exceeds the 10 stream launches it replaces) => small batches only.
   static const int64_t graph_max_frames = getenv("VINSAT_GRAPH_MAX_FRAMES") ? atoll(getenv("VINSAT_GRAPH_MAX_FRAMES")) : 200000;
-  if (!no_graph && b->T <= graph_max_frames && !ctx->timing && !b->window && lam_dev_in == b->lam_next) {
+  if (!no_graph && b->T <= graph_max_frames && !ctx->timing && !b->window && lam_dev_in == b->lam_next && !b->reg_iter) {
     if (!b->st_base) { b->st_base = b->st; b->r_base = b->r; }
     const uint64_t key = (uint64_t)(iter & 0xffff) | ((uint64_t)(initialize ? 1 : 0) << 16) | ((uint64_t)(mode & 0xf) << 17) |
                          ((uint64_t)(b->st == b->st_base ? 1 : 0) << 21) | ((uint64_t)(b->r == b->r_base ? 1 : 0) << 22) |
@@ -534,6 +540,40 @@ int vinsat_batch_ba_iterate(vinsat_batch* b, int iter, int initialize, int mode,
     VS_CUDA(ctx, cudaMemcpyAsync(ntrials_out, b->ntrials, b->P * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return VINSAT_OK;
+}
+
+int vinsat_batch_set_prior(vinsat_batch* b, int mem, const double* states_prior, const double* hessian_state,
+                           const double* hessian_rot) {
+  if (!b || !states_prior || !hessian_state || !hessian_rot)
+    return set_error(b ? b->ctx : nullptr, VINSAT_EINVAL, "vinsat_batch_set_prior: NULL argument");
+  vinsat_ctx* ctx = b->ctx;
+  VS_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int64_t T = b->T;
+  if (!b->pr_st) {
+    VS_CUDA(ctx, cudaMalloc((void**)&b->pr_st, T * 10 * sizeof(double)));
+    VS_CUDA(ctx, cudaMalloc((void**)&b->pr_Hs, T * 36 * sizeof(double)));
+    VS_CUDA(ctx, cudaMalloc((void**)&b->pr_Hr, T * 9 * sizeof(double)));
+    VS_CUDA(ctx, cudaMalloc((void**)&b->e_pr_init, T * sizeof(double)));
+    VS_CUDA(ctx, cudaMalloc((void**)&b->e_pr, T * sizeof(double)));
+  }
+  const cudaMemcpyKind kind = mem == VINSAT_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  VS_CUDA(ctx, cudaMemcpyAsync(b->pr_st, states_prior, T * 10 * sizeof(double), kind, ctx->stream));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->pr_Hs, hessian_state, T * 36 * sizeof(double), kind, ctx->stream));
+  VS_CUDA(ctx, cudaMemcpyAsync(b->pr_Hr, hessian_rot, T * 9 * sizeof(double), kind, ctx->stream));
+  VS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return VINSAT_OK;
+}
+
+int vinsat_batch_ba_reg_iterate(vinsat_batch* b, int iter, int mode, double* lamda_io, int32_t* ntrials_out) {
+  if (!b || !lamda_io) return set_error(b ? b->ctx : nullptr, VINSAT_EINVAL, "vinsat_batch_ba_reg_iterate: NULL argument");
+  vinsat_ctx* ctx = b->ctx;
+  if (!b->pr_st) return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_set_prior has not been called");
+  if (b->window) return set_error(ctx, VINSAT_EINVAL, "BA_reg is not available on frame-window shards");
+  b->reg_iter = true;
+  const int rc = vinsat_batch_ba_iterate(b, iter, 0, mode, lamda_io, ntrials_out);
+  b->reg_iter = false;
+  // the trial that produced r_next used the same projection, so the residual reuse of the next call stays valid
+  return rc;
 }
 
 int vinsat_batch_od_solve(vinsat_batch* b, int num_iters, int n_init, double lamda_init, int mode) {

@@ -102,6 +102,9 @@ struct vinsat_batch {
   int32_t* la_chain = nullptr;        // {0, S_total, 0}
   // ---- Monte-Carlo noise sweeps (mc.cu): true states / pixels the perturbations are drawn around, error scratch ----
   double *mc_st_true = nullptr, *mc_uv_true = nullptr, *mc_vel_true = nullptr, *mc_err = nullptr;
+  // ---- BA_reg (prior.cu): prior states / information matrices and the per-frame sums of |r_prior| ----
+  double *pr_st = nullptr, *pr_Hs = nullptr, *pr_Hr = nullptr, *e_pr_init = nullptr, *e_pr = nullptr;
+  bool reg_iter = false;       // the BA() call in flight is a BA_reg() call (prior terms on)
   bool in_arena = false;       // device buffers come from ctx->arena (never cudaFree'd individually)
   bool have_iter = false;
   bool srec_valid = false;

@@ -460,15 +460,17 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_init_residual(int P, 
                                                        double sqrt_sigma, const double* __restrict__ lam_in,
                                                        double* __restrict__ lam, double* __restrict__ init_res,
                                                        int32_t* __restrict__ active, int32_t* __restrict__ ntrials,
-                                                       const int32_t* __restrict__ gate) {
+                                                       const int32_t* __restrict__ gate,
+                                                       const double* __restrict__ e_prior) {
   if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   __shared__ double s_part[32];
   const int p = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kPT);
   const int lane = threadIdx.x % kPT;
   if (p >= P) return;                    // whole groups leave together (kPT divides blockDim.x)
   const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
-  double so = 0.0, sd = 0.0;
+  double so = 0.0, sd = 0.0, sp = 0.0;
   for (int64_t f = f0 + lane; f < f1; f += kPT) {
+    if (e_prior) sp += e_prior[f];        // BA_reg: r_prior enters unscaled, 7 components per frame (BA_filtering.py:163)
     so += grec[f * VS_GREC + 27];
     if (!initialize && gap[f] > 0) {
       const double* d = drec + f * VS_DREC + 36;
@@ -477,26 +479,28 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_init_residual(int P, 
   }
   so = group_total<kPT>(so, s_part);
   sd = group_total<kPT>(sd, s_part);
+  if (e_prior) sp = group_total<kPT>(sp, s_part);
   if (lane == 0) {
-    const double n = 2.0 * (double)(obs_off[p + 1] - obs_off[p]) + (initialize ? 6.0 : 7.0) * (double)max((long long)(f1 - f0 - 1), 0ll);
-    init_res[p] = (so + sqrt_sigma * sd) / n;
+    const double n = 2.0 * (double)(obs_off[p + 1] - obs_off[p]) + (initialize ? 6.0 : 7.0) * (double)max((long long)(f1 - f0 - 1), 0ll)
+                     + (e_prior ? 7.0 * (double)(f1 - f0) : 0.0);
+    init_res[p] = (so + sqrt_sigma * sd + sp) / n;
     lam[p] = lam_in[p];
     active[p] = (f1 > f0) ? 1 : 0;
     ntrials[p] = 0;
   }
 }
 
-int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double, const double* d_lam_in) {
+int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double, const double* d_lam_in, const double* e_prior) {
   vinsat_ctx* ctx = b->ctx;
   if (b->P == 0) return VINSAT_OK;
   if (b->T > 4096 * b->P) {              // long arcs: one CTA per problem
     VS_LAUNCH(ctx, F_ACCEPT, k_init_residual<1024>, (unsigned)b->P, 1024, 0, (int)b->P, b->d_frame_off,
               b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
-              b->active, b->ntrials, b->gate_arg);
+              b->active, b->ntrials, b->gate_arg, e_prior);
   } else {
     VS_LAUNCH(ctx, F_ACCEPT, k_init_residual<32>, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off,
               b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
-              b->active, b->ntrials, b->gate_arg);
+              b->active, b->ntrials, b->gate_arg, e_prior);
   }
   return VINSAT_OK;
 }
@@ -511,7 +515,7 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_accept(int P, const i
                                                 const double* __restrict__ init_res, double* __restrict__ lam,
                                                 double* __restrict__ lam_next, int32_t* __restrict__ active,
                                                 int32_t* __restrict__ ntrials, int32_t* __restrict__ flags,
-                                                const int32_t* __restrict__ gate) {
+                                                const int32_t* __restrict__ gate, const double* __restrict__ e_prior) {
   if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   __shared__ double s_part[32];
   const int p = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kPT);
@@ -519,18 +523,21 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_accept(int P, const i
   if (p >= P) return;
   if (!active[p]) return;                // uniform over the group
   const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
-  double so = 0.0, sd = 0.0;
+  double so = 0.0, sd = 0.0, sp = 0.0;
   for (int64_t f = f0 + lane; f < f1; f += kPT) {
+    if (e_prior) sp += e_prior[f];
     so += e_obs[f];
     if (!initialize && f + 1 < f1) sd += e_dyn[f];
   }
   so = group_total<kPT>(so, s_part);
   sd = group_total<kPT>(sd, s_part);
+  if (e_prior) sp = group_total<kPT>(sp, s_part);
   if (lane == 0) {
     const unsigned long long wb = wmax[p];
     const double invw = wb ? 1.0 / __longlong_as_double((long long)wb) : 0.0;
-    const double n = 2.0 * (double)(obs_off[p + 1] - obs_off[p]) + (initialize ? 6.0 : 7.0) * (double)max((long long)(f1 - f0 - 1), 0ll);
-    const double residual = (invw * so + sqrt_sigma * sd) / n;
+    const double n = 2.0 * (double)(obs_off[p + 1] - obs_off[p]) + (initialize ? 6.0 : 7.0) * (double)max((long long)(f1 - f0 - 1), 0ll)
+                     + (e_prior ? 7.0 * (double)(f1 - f0) : 0.0);
+    const double residual = (invw * so + sqrt_sigma * sd + sp) / n;
     const double l = lam[p] * 10.0;                       // :72
     lam[p] = l;
     ntrials[p] += 1;
@@ -544,17 +551,17 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_accept(int P, const i
   }
 }
 
-int launch_accept(vinsat_batch* b, int initialize, double Sigma) {
+int launch_accept(vinsat_batch* b, int initialize, double Sigma, const double* e_prior) {
   vinsat_ctx* ctx = b->ctx;
   if (b->P == 0) return VINSAT_OK;
   if (b->T > 4096 * b->P) {
     VS_LAUNCH(ctx, F_ACCEPT, k_accept<1024>, (unsigned)b->P, 1024, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
               b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
-              b->ntrials, b->flags, b->gate_arg);
+              b->ntrials, b->flags, b->gate_arg, e_prior);
   } else {
     VS_LAUNCH(ctx, F_ACCEPT, k_accept<32>, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
               b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
-              b->ntrials, b->flags, b->gate_arg);
+              b->ntrials, b->flags, b->gate_arg, e_prior);
   }
   return VINSAT_OK;
 }

@@ -47,11 +47,14 @@ int launch_select_hist(vinsat_batch* b, int pass);               // histogram of
 int launch_select_pick(vinsat_batch* b, int pass);               // narrow the prefix from sel_hist (and zero it)
 int launch_system_build(vinsat_batch* b, int initialize, double Sigma, double vel_coeff);
 int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double lamda_host_default,
-                         const double* d_lam_in);
+                         const double* d_lam_in, const double* e_prior = nullptr);
 int launch_solve_retract(vinsat_batch* b, int initialize);
 int launch_solve_init_only(vinsat_batch* b);
 int launch_retract_only(vinsat_batch* b);
-int launch_accept(vinsat_batch* b, int initialize, double Sigma);
+int launch_accept(vinsat_batch* b, int initialize, double Sigma, const double* e_prior = nullptr);
+// ---- prior.cu (BA_reg) ----
+int launch_prior_linearize(vinsat_batch* b, double vc, double qc);   // srec += prior blocks; e_pr_init[f] = sum |r_prior|
+int launch_prior_trial(vinsat_batch* b, double vc, double qc);       // e_pr[f] = sum |r_prior(st_new)|
 int launch_gather_last_hessian(vinsat_batch* b, double* out_dev);    // out[P][81] = JTwJ[-9:, -9:] incl. damping
 int launch_stream_gather(vinsat_ctx* ctx, int64_t n, const double* chain, const int64_t* time_idx, int64_t f0, int64_t t0,
                          double* st, double* vel, double* seed);
