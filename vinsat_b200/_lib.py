@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvinsat_b200.so")
+LIB_PATH = os.environ.get("VINSAT_LIB") or os.path.join(_HERE, "libvinsat_b200.so")     # VINSAT_LIB: A/B builds of the kernels
 
 MEM_HOST, MEM_DEVICE = 0, 1
 MODE_STEP1S, MODE_SKIP100 = 0, 1

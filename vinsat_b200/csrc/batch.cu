@@ -38,7 +38,7 @@ int dev_alloc(vinsat_ctx* ctx, T** p, int64_t n) {
 
 void free_all(vinsat_batch* b) {
   void* ptrs[] = {b->st, b->st_new, b->intr, b->crot, b->gap, b->fprob, b->dyn_order, b->obs_start, b->grec, b->drec, b->mrec,
-                  b->srec, b->wrec, b->delta, b->e_obs, b->e_dyn, b->X, b->uv, b->conf, b->oframe, b->r, b->r_next, b->wu,
+                  b->srec, b->wrec, b->delta, b->zeros, b->e_obs, b->e_dyn, b->X, b->uv, b->conf, b->oframe, b->r, b->r_next, b->wu,
                   b->d_frame_off, b->d_obs_off, b->c_obs, b->wmax, b->lam, b->lam_next, b->lam32_last, b->init_res,
                   b->active, b->ntrials, b->sel_prefix, b->sel_rank, b->sel_hist, b->flags, b->seg_a, b->seg_b,
                   b->seg_left, b->seg_prob, b->seg_has_next, b->pl_a, b->pl_b, b->pl_prob, b->red_a, b->red_b,
@@ -295,7 +295,7 @@ static int create_impl(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t ow
   if (b->window) { A(la_pack, NS * (VS_RREC + VS_SREC)); A(la_sums, 4); A(la_edge, 20); }
   A(st, T * 10); A(st_new, T * 10); A(intr, T * 4); A(crot, T * 4); A(gap, T); A(fprob, T); A(dyn_order, T);
   A(obs_start, T + 1); A(grec, T * VS_GREC); A(drec, T * VS_DREC); A(mrec, T * VS_MREC); A(srec, T * VS_SREC); A(wrec, T * VS_WREC);
-  A(delta, T * 9); A(e_obs, T); A(e_dyn, T);
+  A(delta, T * 9); A(e_obs, T); A(e_dyn, T); A(zeros, 64);
   A(X, M * 3); A(uv, M * 2); A(conf, M); A(oframe, M); A(r, M * 2); A(r_next, M * 2); A(wu, M);
   A(d_frame_off, P + 1); A(d_obs_off, P + 1); A(c_obs, P); A(wmax, P); A(lam, P); A(lam_next, P); A(lam32_last, P);
   A(init_res, P); A(active, P); A(ntrials, P); A(sel_prefix, P); A(sel_rank, P); A(sel_hist, P * 2048); A(flags, 4);
@@ -307,6 +307,7 @@ static int create_impl(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t ow
   if (rc == VINSAT_OK) {
     cudaMemsetAsync(b->sel_hist, 0, (size_t)P * 2048 * sizeof(unsigned int), ctx->stream);
     cudaMemsetAsync(b->e_obs, 0, (size_t)T * sizeof(double), ctx->stream);
+    cudaMemsetAsync(b->zeros, 0, 64 * sizeof(double), ctx->stream);
     cudaMemsetAsync(b->e_dyn, 0, (size_t)T * sizeof(double), ctx->stream);
     cudaMemsetAsync(b->drec, 0, (size_t)T * VS_DREC * sizeof(double), ctx->stream);
     rc = do_upload(b, d);

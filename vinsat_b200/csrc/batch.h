@@ -34,6 +34,7 @@ struct vinsat_batch {
   double* srec = nullptr;      // [T][VS_SREC]
   double* wrec = nullptr;      // [T][VS_WREC]
   double* delta = nullptr;     // [T][9]
+  double* zeros = nullptr;     // [64] zero page read by lanes of the fused sweep that have no term of a kind
   // ---- partitioned block-tridiagonal solve (kernels_chain.cu) ----
   bool partitioned = false;
   int64_t n_seg = 0;

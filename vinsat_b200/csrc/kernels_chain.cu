@@ -77,6 +77,7 @@ struct FusedSrc {
   const double* mrec = nullptr;
   const int32_t* gap = nullptr;
   const unsigned long long* wmax = nullptr;   // [P] bit pattern of the largest raw weight
+  const double* zeros = nullptr;              // >= 64 zero doubles: what a lane reads where it has no term
   double Sigma = 0.0, vc = 100.0;
 };
 
@@ -133,13 +134,89 @@ struct FusedRaw {
   int gn, gp;     // gap[f], gap[f-1] (0 at the first frame)
 };
 
+// A/B switches of the round-2 experiments on this kernel (B200, P=1024: baseline 9.59 ms per step of sweeps):
+//   VS_SWEEP_SPARSE_MATVEC=1  skip the 36 structurally zero products of Lo x [W | y]                      -> 9.03 ms (default)
+//   VS_SWEEP_UNPRED_LOADS=1   unpredicated record loads through a zero page (no CS2R / predicates)        -> 11.6 ms (rejected)
+//   (one merged select chain for the diagonal additions instead of two: 10.9 ms, rejected and removed)
+// The kernel is a single dependent-issue stream per scheduler; what ptxas makes of a change decides more than the
+// instruction count does.
+#ifndef VS_SWEEP_UNPRED_LOADS
+#define VS_SWEEP_UNPRED_LOADS 0
+#endif
+#ifndef VS_SWEEP_SPARSE_MATVEC
+#define VS_SWEEP_SPARSE_MATVEC 1
+#endif
+#if VS_SWEEP_UNPRED_LOADS
+struct FusedLane {   // loop-invariant lane constants
+  // Every lane reads the same NUMBER of values per frame; a lane that has no term of a kind reads zeros instead
+  // (base = the zero page, stride 0), so that the loop body carries no predicates and no register zero-fills.
+  const double *gb, *mb, *hb, *xb;     // bases of the four sources (record array or zero page), offsets folded in
+  int gs, ms, hs_rec, xs_rec;          // record strides (0 for the zero page)
+  int gi[6];                           // grec indices of the lane's column
+  int hs, xs;                          // element strides inside a record
+  bool isb, pos, rot, pv, xprev;       // xprev: the coupling source is the PREVIOUS frame's record
+};
+
+__device__ __forceinline__ FusedLane fused_lane(const FusedSrc& S, const int l, const int dir) {
+  FusedLane L;
+  L.isb = l == 9; L.pos = l < 3; L.rot = l >= 3 && l < 6; L.pv = (l < 9) && !L.rot;
+  const int pl = L.pos ? l : l - 3, cl = l - 3;
+  const bool pg = l < 6 || L.isb, pm = L.pv || L.isb, ph = L.rot || L.isb;
+#pragma unroll
+  for (int j = 0; j < 6; j++) L.gi[j] = pg ? (L.isb ? 21 + j : (j <= l ? sym6(j, l) : sym6(l, j))) : j;
+  L.gb = pg ? S.grec : S.zeros;  L.gs = pg ? VS_GREC : 0;
+  L.mb = pm ? S.mrec + (L.isb ? 36 : pl * 6) : S.zeros;  L.ms = pm ? VS_MREC : 0;
+  L.hb = ph ? S.drec + (L.rot ? 46 + cl : 43) : S.zeros;  L.hs_rec = ph ? VS_DREC : 0;
+  L.hs = ph ? (L.rot ? 3 : 1) : 1;
+  // coupling block: Phi entries (pos / vel), Hq_off column (rot), r of the pair before (b)
+  int xo;
+  if (L.isb) { xo = 36; L.xs = 1; }
+  else if (L.rot) { xo = dir > 0 ? 55 + cl : 55 + cl * 3; L.xs = dir > 0 ? 3 : 1; }
+  else { xo = dir > 0 ? pl * 6 : pl; L.xs = dir > 0 ? 1 : 6; }
+  L.xb = S.drec + xo;  L.xs_rec = VS_DREC;
+  L.xprev = L.isb || dir < 0;
+  return L;
+}
+
+__device__ __forceinline__ void fused_load(const FusedSrc& S, const FusedLane& L, const int64_t f, const int dir,
+                                           FusedRaw& R) {
+  const double* G = L.gb + f * L.gs;
+  const double* Dr = L.hb + f * L.hs_rec;
+  const double* Mm = L.mb + f * L.ms;
+  // coupling block: this frame's record (forward) or the previous frame's (reverse; also r of the pair before).  At
+  // the first frame there is no previous pair: frame 0's own record is read instead and multiplied by a zero
+  // coefficient in fused_combine (gp == 0 there), so no predicate is needed.
+  const int64_t fx = L.xprev ? (f > 0 ? f - 1 : 0) : f;
+  const double* Dx = L.xb + fx * L.xs_rec;
+  R.gn = S.gap[f];
+  R.gp = f > 0 ? S.gap[f - 1] : 0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    R.g[j] = G[L.gi[j]];
+    R.m[j] = Mm[j];
+  }
+  // rot lanes have three coupling values; their x[3..5] would be multiplied by zero: not loaded
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    R.x[j] = Dx[j * L.xs];
+    R.h[j] = Dr[j * L.hs];
+  }
+  if (!L.rot) {
+#pragma unroll
+    for (int j = 3; j < 6; j++) R.x[j] = Dx[j * L.xs];
+  } else {
+    R.x[3] = 0.0; R.x[4] = 0.0; R.x[5] = 0.0;
+  }
+}
+
+#else
 struct FusedLane {   // loop-invariant lane constants
   int gi[6];
   int mo, ho, hs, xo, xs, xn;
   bool pg, pm, ph, isb, pos, rot, pv;
 };
 
-__device__ __forceinline__ FusedLane fused_lane(const int l, const int dir) {
+__device__ __forceinline__ FusedLane fused_lane(const FusedSrc&, const int l, const int dir) {
   FusedLane L;
   L.isb = l == 9; L.pos = l < 3; L.rot = l >= 3 && l < 6; L.pv = (l < 9) && !L.rot;
   const int pl = L.pos ? l : l - 3, cl = l - 3;
@@ -176,8 +253,9 @@ __device__ __forceinline__ void fused_load(const FusedSrc& S, const FusedLane& L
   for (int j = 0; j < 3; j++) R.h[j] = L.ph ? Dr[L.ho + j * L.hs] : 0.0;
 }
 
-__device__ __forceinline__ void fused_combine(const FusedSrc& S, const FusedLane& L, const FusedRaw& R, const int l,
-                                              const int dir, const double invw, double (&out0)[9], double (&out1)[9]) {
+#endif
+__device__ __forceinline__ double fused_combine(const FusedSrc& S, const FusedLane& L, const FusedRaw& R, const int l,
+                                                const int dir, const double invw, double (&out0)[9], double (&out1)[9]) {
   const bool hn = R.gn > 0, hp = R.gp > 0;
   const double vc2 = S.vc * S.vc;
   const double sN = hn ? (L.isb ? -S.Sigma : S.Sigma) : 0.0;
@@ -203,6 +281,36 @@ __device__ __forceinline__ void fused_combine(const FusedSrc& S, const FusedLane
     out1[j] = cp * R.x[j];
     out1[3 + j] = cr * R.x[j];
     out1[6 + j] = cv * R.x[3 + j];
+  }
+  return 0.0;
+}
+
+// corr = Lo x v for the BA system's lower blocks: Lo = U^T couples position / velocity rows only with position /
+// velocity columns and rotation rows only with rotation columns, so 45 of the 81 products are zero.
+// M[k*kMS + r] = Lo[r][k] as in matvec9.
+__device__ __forceinline__ void matvec9_pv_rot(const double* __restrict__ M, const double* v, double* out) {
+#pragma unroll
+  for (int r = 0; r < 9; r++) out[r] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const double vk = v[k];
+    const double* row = M + k * kMS;
+    if (k >= 3 && k < 6) {
+      const double2 a = *reinterpret_cast<const double2*>(row + 2);      // [2], [3]
+      const double2 b = *reinterpret_cast<const double2*>(row + 4);      // [4], [5]
+      out[3] = fma(a.y, vk, out[3]);
+      out[4] = fma(b.x, vk, out[4]);
+      out[5] = fma(b.y, vk, out[5]);
+    } else {
+      const double2 a = *reinterpret_cast<const double2*>(row);          // [0], [1]
+      const double2 b = *reinterpret_cast<const double2*>(row + 6);      // [6], [7]
+      out[0] = fma(a.x, vk, out[0]);
+      out[1] = fma(a.y, vk, out[1]);
+      out[2] = fma(row[2], vk, out[2]);
+      out[6] = fma(b.x, vk, out[6]);
+      out[7] = fma(b.y, vk, out[7]);
+      out[8] = fma(row[8], vk, out[8]);
+    }
   }
 }
 
@@ -410,7 +518,7 @@ __global__ void __launch_bounds__(kF3Warps * 32, MINB) k_chain_forward3(ChainArg
   }
   FusedLane FL;
   FusedRaw FR;
-  if (FUSED) FL = fused_lane(l, dir);
+  if (FUSED) FL = fused_lane(A.fs, l, dir);
   if (len > 0) {
     if (FUSED) {
       fused_load(A.fs, FL, a, dir, FR);
@@ -495,7 +603,8 @@ __global__ void __launch_bounds__(kF3Warps * 32, MINB) k_chain_forward3(ChainArg
       double v[9];
 #pragma unroll
       for (int k = 0; k < 9; k++) v[k] = isS ? av[1][k] : av[0][k];
-      matvec9(M, v, corr0);
+      if (FUSED && VS_SWEEP_SPARSE_MATVEC) matvec9_pv_rot(M, v, corr0);
+      else matvec9(M, v, corr0);
       if (SPIKE) matvec9(M, av[NS - 1], corr2);
       if (!more && writer) {
         if (midrec) {
@@ -898,7 +1007,7 @@ int launch_chain_solve(vinsat_batch* b) {
       A.gate = b->gate_arg;
       if (b->fused_system) {
         A.fused = 1; A.rec = nullptr;
-        A.fs.grec = b->grec; A.fs.drec = b->drec; A.fs.mrec = b->mrec; A.fs.gap = b->gap; A.fs.wmax = b->wmax;
+        A.fs.grec = b->grec; A.fs.drec = b->drec; A.fs.mrec = b->mrec; A.fs.gap = b->gap; A.fs.wmax = b->wmax; A.fs.zeros = b->zeros;
         A.fs.Sigma = b->cur_sigma; A.fs.vc = b->cur_vc;
       }
     }
