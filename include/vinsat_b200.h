@@ -252,7 +252,9 @@ enum {
   VINSAT_LA_RESID = 0, VINSAT_LA_SELECT_BEGIN, VINSAT_LA_SELECT_HIST, VINSAT_LA_SELECT_PICK, VINSAT_LA_ASSEMBLE,
   VINSAT_LA_DYNAMICS, VINSAT_LA_SYSTEM, VINSAT_LA_SUMS_INIT, VINSAT_LA_SET_LAM, VINSAT_LA_SOLVE_INIT,
   VINSAT_LA_FORWARD, VINSAT_LA_REDUCED, VINSAT_LA_BACKSUB, VINSAT_LA_RETRACT, VINSAT_LA_PACK_EDGES,
-  VINSAT_LA_APPLY_GHOSTS, VINSAT_LA_TRIAL, VINSAT_LA_SUMS_TRIAL, VINSAT_LA_COMMIT
+  VINSAT_LA_APPLY_GHOSTS, VINSAT_LA_TRIAL, VINSAT_LA_SUMS_TRIAL, VINSAT_LA_COMMIT,
+  /* device-side LM bookkeeping (lets one iteration be captured as one CUDA graph, kernels + NCCL): */
+  VINSAT_LA_BEGIN_ITER, VINSAT_LA_ACCEPT, VINSAT_LA_COMMIT_COPY
 };
 enum {
   VINSAT_LA_BUF_HIST = 0,   /* uint32[2048]   all-reduce SUM between SELECT_HIST and SELECT_PICK */
@@ -261,7 +263,10 @@ enum {
   VINSAT_LA_BUF_PACK,       /* float64[n_seg*514]  all-gather into GATHER after FORWARD */
   VINSAT_LA_BUF_GATHER,     /* float64[S_total*514] */
   VINSAT_LA_BUF_EDGE,       /* float64[20]    all-gather into EDGES_ALL after PACK_EDGES */
-  VINSAT_LA_BUF_EDGES_ALL   /* float64[n_ranks*20] */
+  VINSAT_LA_BUF_EDGES_ALL,  /* float64[n_ranks*20] */
+  VINSAT_LA_BUF_FLAGS,      /* int32[4]: [0] = 1 while the LM loop of the iteration wants another trial */
+  VINSAT_LA_BUF_LAM_NEXT,   /* float64[1]: lamda_init of the next BA call */
+  VINSAT_LA_BUF_NTRIALS     /* int32[1] */
 };
 int vinsat_la_stage(vinsat_batch* b, int stage, int64_t i0, int64_t i1, double d0);
 int vinsat_la_ptr(vinsat_batch* b, int which, void** ptr, int64_t* count);

@@ -32,21 +32,34 @@ def main():
     pr = synth.make_problem(123, T, K, gap_max=3 if T > 5000 else 20)
     la = longarc.LongArc(pr, ctxs=[ctx], use_dist=world > 1, world=world)
     n_init = min(10, iters // 2)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    lam = 1e-4
-    sched = []
-    for it in range(iters):
-        lam, ntr = la.ba_iterate(it, lam, initialize=it < n_init)
-        sched.append((lam, ntr))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    dt = time.perf_counter() - t0
+    graphs = la.enable_graphs() and os.environ.get("VINSAT_LA_HOST_LM") is None
+
+    def solve():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        lam = 1e-4
+        sched = []
+        for it in range(iters):
+            if graphs:
+                lam, ntr = la.ba_iterate_device_lm(it, 1e-4 if it == 0 else None, initialize=it < n_init)
+            else:
+                lam, ntr = la.ba_iterate(it, lam, initialize=it < n_init)
+            sched.append((lam, ntr))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return time.perf_counter() - t0, sched
+
+    dt_first, sched = solve()
+    la.reset_states()
+    dt, sched_b = solve()                      # second solve: every CUDA graph replays
+    assert sched == sched_b
     st = la.gather_states()
     out = dict(world=world, T=T, M=T * K, iters=iters, seconds=dt, ms_per_iteration=1e3 * dt / iters,
+               first_solve_ms_per_iteration=1e3 * dt_first / iters, device_lm_and_graphs=bool(graphs and la.use_graphs),
+               graph_error=getattr(la, "graph_error", None), graph_replays=getattr(la, "n_graph_replays", 0),
                segments_per_rank=la.S, collectives=la.n_collectives,
                max_pos_err_vs_truth_km=float(np.abs(st[:, :3] - pr["states_gt"][:, :3]).max()))
     if rank == 0:

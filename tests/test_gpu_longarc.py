@@ -65,3 +65,46 @@ def test_window_plan():
     assert a["obs_off"][1] == 8 and a["ii"].min() == 1 and a["ii"].max() == 4
     a, lo, hi = longarc.window_arrays(pr, 0, 4)
     assert a["frame_off"][1] == 5 and (lo, hi) == (0, 4)
+
+
+def test_device_side_lm_and_cuda_graphs_equal_host_driven_iterations():
+    """The long-arc iteration with the LM bookkeeping on the device and the head / extra trials replayed as CUDA graphs
+    (world = 1 here; the NCCL collectives are captured the same way on N > 1, tests/run_longarc_nccl.py): same LM
+    schedule and states as the host-driven `ba_iterate`, on a noisy problem whose LM loop rejects trials; a second solve
+    after `reset_states` (all replays) is bit-identical to the first."""
+    import torch
+    from vinsat_b200 import _lib
+    ctx = _lib.Context(0)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx._bound_to_torch = True
+    try:
+        pr = synth.make_problem(79, 150, 6, sigma_px=25.0, gap_max=40)
+        ref = longarc.LongArc(pr, ctxs=[ctx], world=1, n_segments=3)
+        lam, sched_ref = 1e-4, []
+        for it in range(20):
+            lam, ntr = ref.ba_iterate(it, lam, initialize=it < 10)
+            sched_ref.append((lam, ntr))
+        st_ref = ref.gather_states()
+        ref.close()
+        assert max(n for _, n in sched_ref) > 1, "no LM rejection: the extra-trial graph would be untested"
+        la = longarc.LongArc(pr, ctxs=[ctx], world=1, n_segments=3)
+        assert la.enable_graphs()
+        for rep in range(2):
+            sched = []
+            for it in range(20):
+                lam, ntr = la.ba_iterate_device_lm(it, 1e-4 if it == 0 else None, initialize=it < 10)
+                sched.append((lam, ntr))
+            st = la.gather_states()
+            assert sched == sched_ref, rep
+            assert np.abs(st - st_ref).max() < 1e-9, rep
+            if rep == 0:
+                st0 = st
+                la.reset_states()
+        assert np.array_equal(st, st0)
+        assert la.graph_error is None and la.use_graphs and la.n_graph_replays > 20
+        la.close()
+    finally:
+        torch.cuda.set_stream(torch.cuda.default_stream())
+        ctx.close()

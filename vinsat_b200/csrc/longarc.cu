@@ -74,6 +74,30 @@ __global__ void k_la_set_lam(double lam_v, double* __restrict__ lam, int32_t* __
   active[0] = 1;
 }
 
+// Device-side LM bookkeeping, so that a whole iteration (kernels + NCCL exchanges) can be ONE CUDA graph: the damping
+// never passes through the host.  begin: lam <- lam_next (what the previous BA call handed on, BA_filtering.py:79).
+__global__ void k_la_begin_iter(const double* __restrict__ lam_next, double* __restrict__ lam, int32_t* __restrict__ active,
+                                int32_t* __restrict__ ntrials, int32_t* __restrict__ flags) {
+  lam[0] = lam_next[0];
+  active[0] = 1;
+  ntrials[0] = 0;
+  flags[0] = 1;
+}
+
+// accept test on the all-reduced sums (identical on every rank): BA_filtering.py:51,66-79
+__global__ void k_la_accept(const double* __restrict__ sums, double n, double sqrt_sigma, double* __restrict__ init_res,
+                            double* __restrict__ lam, double* __restrict__ lam_next, int32_t* __restrict__ ntrials,
+                            int32_t* __restrict__ flags) {
+  if (ntrials[0] == 0) init_res[0] = (sums[0] + sqrt_sigma * sums[1]) / n;
+  const double residual = (sums[2] + sqrt_sigma * sums[3]) / n;
+  const double l = lam[0] * 10.0;
+  lam[0] = l;
+  ntrials[0] += 1;
+  const bool done = (residual < init_res[0]) || (l > 1e4);
+  flags[0] = done ? 0 : 1;
+  if (done) lam_next[0] = fmax(fmin(1e-1, l * 0.01), 1e-4);
+}
+
 __global__ void __launch_bounds__(256) k_la_pack(int n_seg, const int32_t* __restrict__ seg_b,
                                                  const double* __restrict__ redrec, const double* __restrict__ srec,
                                                  double* __restrict__ pack) {
@@ -154,6 +178,9 @@ int vinsat_la_ptr(vinsat_batch* b, int which, void** ptr, int64_t* count) {
     case VINSAT_LA_BUF_GATHER: *ptr = b->la_gath; *count = b->S_total * kPack; break;
     case VINSAT_LA_BUF_EDGE: *ptr = b->la_edge; *count = 20; break;
     case VINSAT_LA_BUF_EDGES_ALL: *ptr = b->la_edges_all; *count = b->n_ranks * 20; break;
+    case VINSAT_LA_BUF_FLAGS: *ptr = b->flags; *count = 4; break;                     // int32: [0] = LM loop still active
+    case VINSAT_LA_BUF_LAM_NEXT: *ptr = b->lam_next; *count = 1; break;               // float64
+    case VINSAT_LA_BUF_NTRIALS: *ptr = b->ntrials; *count = 1; break;                 // int32
     default: return set_error(b->ctx, VINSAT_EINVAL, "vinsat_la_ptr: unknown buffer %d", which);
   }
   if (!*ptr) return set_error(b->ctx, VINSAT_EINVAL, "vinsat_la_ptr: buffer %d not allocated yet", which);
@@ -220,6 +247,17 @@ int vinsat_la_stage(vinsat_batch* b, int stage, int64_t i0, int64_t i1, double d
       return VINSAT_OK;
     case VINSAT_LA_COMMIT:
       std::swap(b->st, b->st_new);
+      return VINSAT_OK;
+    case VINSAT_LA_BEGIN_ITER:                                                     // d0 >= 0: also (re)sets lam_next from the host
+      if (d0 > 0.0) VS_LAUNCH(ctx, F_ACCEPT, k_la_set_lam, 1, 1, 0, d0, b->lam_next, b->active);
+      VS_LAUNCH(ctx, F_ACCEPT, k_la_begin_iter, 1, 1, 0, b->lam_next, b->lam, b->active, b->ntrials, b->flags);
+      return VINSAT_OK;
+    case VINSAT_LA_ACCEPT:                                                         // i1 = number of residual components, d0 = sqrt(Sigma)
+      VS_LAUNCH(ctx, F_ACCEPT, k_la_accept, 1, 1, 0, b->la_sums, (double)i1, d0, b->init_res, b->lam, b->lam_next, b->ntrials,
+                b->flags);
+      return VINSAT_OK;
+    case VINSAT_LA_COMMIT_COPY:                                                    // graph mode: fixed buffer roles, copy instead of swap
+      VS_CUDA(ctx, cudaMemcpyAsync(b->st, b->st_new, b->T * 10 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
       return VINSAT_OK;
     default: return set_error(ctx, VINSAT_EINVAL, "vinsat_la_stage: unknown stage %d", stage);
   }

@@ -26,9 +26,9 @@ import numpy as np
 from . import _lib
 
 (RESID, SELECT_BEGIN, SELECT_HIST, SELECT_PICK, ASSEMBLE, DYNAMICS, SYSTEM, SUMS_INIT, SET_LAM, SOLVE_INIT, FORWARD,
- REDUCED, BACKSUB, RETRACT, PACK_EDGES, APPLY_GHOSTS, TRIAL, SUMS_TRIAL, COMMIT) = range(19)
-BUF_HIST, BUF_WMAX, BUF_SUMS, BUF_PACK, BUF_GATHER, BUF_EDGE, BUF_EDGES_ALL = range(7)
-_TYPESTR = {BUF_HIST: "<i4", BUF_WMAX: "<i8"}
+ REDUCED, BACKSUB, RETRACT, PACK_EDGES, APPLY_GHOSTS, TRIAL, SUMS_TRIAL, COMMIT, BEGIN_ITER, ACCEPT, COMMIT_COPY) = range(22)
+BUF_HIST, BUF_WMAX, BUF_SUMS, BUF_PACK, BUF_GATHER, BUF_EDGE, BUF_EDGES_ALL, BUF_FLAGS, BUF_LAM_NEXT, BUF_NTRIALS = range(10)
+_TYPESTR = {BUF_HIST: "<i4", BUF_WMAX: "<i8", BUF_FLAGS: "<i4", BUF_NTRIALS: "<i4"}
 
 
 def plan_windows(T, world):
@@ -135,6 +135,7 @@ class LongArc:
         for p in self.parts:
             p.alloc_reduced(self.S_total, self.world)
         self.n_collectives = 0
+        self.use_graphs = False
         self._exchange_ghosts(current=True)        # ghost rows came from the host arrays; keeps the code path uniform
 
     # ---- collectives over (local parts x processes) ------------------------------------------------------
@@ -259,11 +260,142 @@ class LongArc:
         self._stage(COMMIT)
         return max(min(1e-1, lam * 0.01), 1e-4), ntrials
 
+    # ---- the same iteration with the LM bookkeeping on the device: one CUDA graph per (alpha, Sigma, phase) -------
+    def _graphable(self):
+        return len(self.parts) == 1          # one window per process (the emulated multi-part mode stages through the host)
+
+    def _issue_trial(self, init, first, n, sq):
+        """Everything of one LM trial, asynchronously (no host decision inside): solve, retract, ghosts, trial residuals,
+        ONE all-reduce of the four sums, device-side accept test."""
+        if init:
+            self._stage(SOLVE_INIT)
+        else:
+            self._stage(FORWARD)
+            self._all_gather(BUF_PACK, BUF_GATHER)
+            self._stage(REDUCED, per_rank_i0=lambda p: p.rank * self.S)
+            self._stage(BACKSUB)
+        self._stage(RETRACT)
+        self._exchange_ghosts(current=False)
+        self._stage(TRIAL, self.mode, init)
+        self._stage(SUMS_TRIAL, init, 0 if first else 1)
+        self._all_reduce(BUF_SUMS, "sum")
+        self._stage(ACCEPT, init, n, sq)
+
+    def _issue_head(self, it, init, alpha, Sigma, n, sq):
+        """Linearisation + first trial (everything up to the first host decision)."""
+        self._stage(BEGIN_ITER)
+        self._stage(RESID)
+        self._stage(SELECT_BEGIN, 2 * self.M)
+        for ps in range(6):
+            self._stage(SELECT_HIST, ps)
+            self._all_reduce(BUF_HIST, "sum")
+            self._stage(SELECT_PICK, ps)
+        self._stage(ASSEMBLE, d0=alpha)
+        self._all_reduce(BUF_WMAX, "max")
+        if not init:
+            self._stage(DYNAMICS, self.mode)
+            self._stage(SYSTEM, 0, 0, Sigma)
+        self._stage(SUMS_INIT, init)
+        self._issue_trial(init, True, n, sq)
+
+    def _run(self, key, issue):
+        """Runs `issue()` as a CUDA graph: the first time a key is seen it runs eagerly (one-time host actions such as
+        function attributes and scratch growth happen there), the second time it is captured -- library launches
+        and NCCL collectives alike -- and from then on replayed."""
+        torch = self.torch
+        if not self.use_graphs:
+            issue()
+            return
+        g = self._graphs.get(key)
+        if g is not None:
+            g.replay()
+            self.n_graph_replays += 1
+            return
+        if key not in self._graph_seen:
+            self._graph_seen.add(key)
+            issue()
+            return
+        (p,) = self.parts
+        try:
+            g = torch.cuda.CUDAGraph()
+            cap = self._capture_stream
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.graph(g, stream=cap):
+                p.ctx.set_stream(cap.cuda_stream)
+                try:
+                    issue()
+                finally:
+                    p.ctx.set_stream(self._home_stream.cuda_stream)
+            self._graphs[key] = g
+            g.replay()
+            self.n_graph_replays += 1
+        except Exception as e:                      # capture not possible here: stay eager from now on
+            self.use_graphs = False
+            self.graph_error = repr(e)[:200]
+            p.ctx.set_stream(self._home_stream.cuda_stream)
+            torch.cuda.synchronize()
+            issue()
+
+    def reset_states(self):
+        """Back to the initial guess (same buffers, so captured graphs stay valid)."""
+        for p in self.parts:
+            p.batch.set_states(p.arrays["states"])
+        self._exchange_ghosts(current=True)
+
+    def enable_graphs(self):
+        """Call once after construction with the context bound to torch's current stream (ctx.set_stream)."""
+        torch = self.torch
+        if not self._graphable() or not getattr(self.parts[0].ctx, "_bound_to_torch", False):
+            return False
+        self._home_stream = torch.cuda.current_stream()
+        self._capture_stream = torch.cuda.Stream(device=self.parts[0].device)
+        self._graphs, self._graph_seen = {}, set()
+        self.n_graph_replays = 0
+        self.graph_error = None
+        self.use_graphs = True
+        self._status = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._lam_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+        return True
+
+    def ba_iterate_device_lm(self, it, lamda_init=None, initialize=False):
+        """`ba_iterate` with the damping / accept logic on the device (stages BEGIN_ITER, ACCEPT, COMMIT_COPY) and the
+        head and the extra trials of an iteration issued as CUDA graphs (`enable_graphs`).  `lamda_init` is only needed
+        for the first call (afterwards the device carries lamda from call to call).  Returns (lamda_next, ntrials)."""
+        torch = self.torch
+        (p,) = self.parts
+        alpha = min(max(1 - (2 * (it / 5) - 1), 1), 2)
+        Sigma = float(min(10000 * (it + 1) ** 2, 1000000))
+        sq = math.sqrt(Sigma)
+        init = 1 if initialize else 0
+        n = int(2 * self.M + (6 if initialize else 7) * max(self.T - 1, 0))
+        if lamda_init is not None:
+            self._stage(BEGIN_ITER, d0=float(lamda_init))        # seeds lam_next; the head's own BEGIN_ITER copies it
+        self._run(("head", alpha, Sigma if not initialize else 0.0, init), lambda: self._issue_head(it, init, alpha, Sigma, n, sq))
+        ntrials = 0
+        while True:
+            self._status.copy_(p.buf(BUF_FLAGS), non_blocking=True)
+            torch.cuda.current_stream().synchronize()            # the ONE host wait of the trial
+            ntrials += 1
+            if int(self._status[0]) == 0:
+                break
+            self._run(("trial", Sigma if not initialize else 0.0, init), lambda: self._issue_trial(init, False, n, sq))
+        self._stage(COMMIT_COPY)
+        self._lam_host.copy_(p.buf(BUF_LAM_NEXT), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self._lam_host[0]), ntrials
+
     def od_solve(self, num_iters=20, n_init=10, lamda_init=1e-4):
         lam = lamda_init
         for it in range(num_iters):
             lam, _ = self.ba_iterate(it, lam, initialize=(it < n_init))
         return lam
+
+    def od_solve_device_lm(self, num_iters=20, n_init=10, lamda_init=1e-4):
+        lam, total = lamda_init, 0
+        for it in range(num_iters):
+            lam, ntr = self.ba_iterate_device_lm(it, lamda_init if it == 0 else None, initialize=(it < n_init))
+            total += ntr
+        return lam, total
 
     def owned_states(self):
         """{rank: states of its owned frames}."""
