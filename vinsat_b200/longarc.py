@@ -168,6 +168,9 @@ class LongArc:
             self._stream_handoff(p)
             self.dist.all_gather_into_tensor(p.buf(dst), p.buf(src))
             return
+        if len(self.parts) == 1 and self.world == 1 and getattr(self.parts[0].ctx, "_bound_to_torch", False):
+            self.parts[0].buf(dst).copy_(self.parts[0].buf(src))      # same stream as the library: ordered, capturable
+            return
         self._sync()
         cat = torch.cat([p.buf(src).to(self.parts[0].device) for p in sorted(self.parts, key=lambda q: q.rank)])
         for p in self.parts:
@@ -320,21 +323,21 @@ class LongArc:
             g = torch.cuda.CUDAGraph()
             cap = self._capture_stream
             cap.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.graph(g, stream=cap):
-                p.ctx.set_stream(cap.cuda_stream)
-                try:
+            p.ctx.set_stream(cap.cuda_stream)       # (synchronises: must happen outside the capture)
+            try:
+                with torch.cuda.graph(g, stream=cap):
                     issue()
-                finally:
-                    p.ctx.set_stream(self._home_stream.cuda_stream)
+            finally:
+                p.ctx.set_stream(self._home_stream.cuda_stream)
             self._graphs[key] = g
             g.replay()
             self.n_graph_replays += 1
-        except Exception as e:                      # capture not possible here: stay eager from now on
+        except Exception as e:
+            # a capture that fails half way leaves this rank's stream (and, with NCCL, the communicator) in an undefined
+            # state while the other ranks carry on: do not try to continue
             self.use_graphs = False
-            self.graph_error = repr(e)[:200]
-            p.ctx.set_stream(self._home_stream.cuda_stream)
-            torch.cuda.synchronize()
-            issue()
+            self.graph_error = repr(e)[:300]
+            raise
 
     def reset_states(self):
         """Back to the initial guess (same buffers, so captured graphs stay valid)."""
