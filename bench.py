@@ -284,7 +284,9 @@ def longarc_leg(ctx, rank, world, max_over_ranks, sync_all, T=100_000, K=50):
         pr = synth.make_problem(123, T, K, gap_max=3)
         ctx._bound_to_torch = True                      # ctx launches on torch's current stream (set by run_gpu)
         la = longarc.LongArc(pr, ctxs=[ctx], use_dist=world > 1, world=world)
-        graphs = la.enable_graphs()
+        # device-side LM + CUDA graphs (kernels and NCCL captured together) is opt-in: measured on 2 x B200 it is SLOWER than the
+        # host-driven exchange at this arc size (2.56 vs 2.10 ms per iteration, profiles/r02_longarc_graphs_n2.json)
+        graphs = bool(os.environ.get("VINSAT_LA_GRAPHS")) and la.enable_graphs()
 
         def solve(timed_full):
             """20 iterations with the LM bookkeeping on the device; returns (seconds, schedule)."""
@@ -294,7 +296,10 @@ def longarc_leg(ctx, rank, world, max_over_ranks, sync_all, T=100_000, K=50):
             for it in range(20):
                 if it >= 10:
                     torch.cuda.synchronize(); t1 = time.perf_counter()
-                lam, ntr = la.ba_iterate_device_lm(it, 1e-4 if it == 0 else None, initialize=it < 10)
+                if graphs:
+                    lam, ntr = la.ba_iterate_device_lm(it, 1e-4 if it == 0 else None, initialize=it < 10)
+                else:
+                    lam, ntr = la.ba_iterate(it, 1e-4 if it == 0 else sched[-1][0], initialize=it < 10)
                 if it >= 10:
                     torch.cuda.synchronize(); timed_full.append(time.perf_counter() - t1)
                 sched.append((lam, ntr))
@@ -324,8 +329,8 @@ def longarc_leg(ctx, rank, world, max_over_ranks, sync_all, T=100_000, K=50):
                "max_pos_err_vs_truth_km": float(np.abs(st[:, :3] - pr["states_gt"][:, :3]).max()),
                "bytes_per_frame_resident": 4152 + 92 * K,
                "capacity_frames_per_gpu_at_170GB": int(170e9 // (4152 + 92 * K)),
-               "note": "LM bookkeeping on the device; head and extra trials of an iteration issued as CUDA graphs (library launches + NCCL "
-                       "collectives captured together); the headline figures are the second, all-replay solve. Per LM trial: 1 all-gather "
+               "note": "headline figures = the second of two identical solves (VINSAT_LA_GRAPHS=1: LM bookkeeping on the device, head and "
+                       "extra trials of an iteration as CUDA graphs with the NCCL collectives captured). Per LM trial: 1 all-gather "
                        "of the per-segment reduced records, 1 all-gather of edge states, 1 all-reduce of 4 sums; per iteration 6 histogram "
                        "all-reduces (exact global median) + 1 all-reduce(MAX); all messages << 1 MB (latency bound)"}
         if rank == 0:

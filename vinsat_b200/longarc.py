@@ -421,6 +421,13 @@ class LongArc:
         return np.concatenate([out[r, :sizes[r]] for r in range(self.world)])
 
     def close(self):
+        # captured graphs hold NCCL kernels: release them (and drain the device) before the batches and, later, the
+        # process group go away
+        if getattr(self, "_graphs", None):
+            self._graphs.clear()
+            import gc
+            gc.collect()
+            self.torch.cuda.synchronize()
         for p in self.parts:
             p.close()
 
