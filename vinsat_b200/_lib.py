@@ -178,6 +178,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for t in self.__dict__.pop("_satcam_tables", {}).values():      # device tables created through this context
+                t.close()
             self.lib.vinsat_ctx_destroy(self.h)
             self.h = None
 

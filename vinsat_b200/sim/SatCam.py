@@ -81,21 +81,18 @@ def region_name(code):
     return None if code < 0 else "%02d%s" % (code // 32, chr(64 + code % 32))
 
 
-_TABLES = {}
-
-
 def landmark_table(ctx, regions=None):
     """Device-resident landmark table (all shipped CSVs) with `regions` as the active set (SatCam.py:63-67);
-    cached per (context, active set)."""
+    cached ON the context per active set (it lives and dies with the context's device memory)."""
     active = tuple(DEFAULT_REGIONS if regions is None else regions)
-    key = (id(ctx), active)
-    if key not in _TABLES:
+    tables = ctx.__dict__.setdefault("_satcam_tables", {})
+    if active not in tables:
         lm = load_landmarks()
         names = sorted(lm)
         off = np.cumsum([0] + [len(lm[n]) for n in names])
         rows = np.concatenate([lm[n][:, :2] for n in names])
-        _TABLES[key] = ctx.satcam_table([region_code(n) for n in names], off, rows, [region_code(n) for n in active])
-    return _TABLES[key]
+        tables[active] = ctx.satcam_table([region_code(n) for n in names], off, rows, [region_code(n) for n in active])
+    return tables[active]
 
 
 class SatCam:
