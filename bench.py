@@ -317,6 +317,7 @@ def longarc_leg(ctx, rank, world, max_over_ranks, sync_all, T=100_000, K=50):
         first_full_ms = max_over_ranks(1e3 * float(np.median(t_first)))
         st = la.gather_states()
         ncoll = la.n_collectives
+        same = bool(np.array_equal(st_first, st) and sched == sched_b)
         la.close()
         out = {"workload": "configs[2]: one arc of %d frames x %d obs/frame (M = %d), frame-window sharded over %d GPU(s), 20 BA iterations"
                            % (T, K, T * K, world),
@@ -324,7 +325,7 @@ def longarc_leg(ctx, rank, world, max_over_ranks, sync_all, T=100_000, K=50):
                "first_solve_ms_per_iteration_mean": 1e3 * first_s / 20, "first_solve_ms_per_full_iteration_median": first_full_ms,
                "cuda_graphs": {"enabled": bool(graphs and la.use_graphs), "replays": getattr(la, "n_graph_replays", 0),
                                "captured": len(getattr(la, "_graphs", {})), "error": getattr(la, "graph_error", None)},
-               "second_solve_equals_first": bool(np.array_equal(st_first, la.gather_states()) and sched == sched_b),
+               "second_solve_equals_first": same,
                "collectives_per_20_iterations": ncoll // 2, "lm_trials": int(sum(n for _, n in sched)),
                "max_pos_err_vs_truth_km": float(np.abs(st[:, :3] - pr["states_gt"][:, :3]).max()),
                "bytes_per_frame_resident": 4152 + 92 * K,
