@@ -11,6 +11,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+_real_stdout = os.dup(1)          # NCCL prints its version banner on fd 1: keep stdout for the ONE JSON record
+os.dup2(2, 1)
+
 from vinsat_b200 import config
 from vinsat_b200.eval import batch_runner
 
@@ -46,12 +49,12 @@ if rank == 0:
     allres = [r for g in gathered for r in g[2]]
     chunks = sorted(r["chunk"] for r in allres)
     assert chunks == list(range(len(chunks))), "every chunk exactly once"
-    print(json.dumps({
+    os.write(_real_stdout, (json.dumps({
         "config": "configs[3]: %d OD problems (1000 frames x 10 obs), noise sweep sigma_px in %s, %d GPU(s), %d solves in flight per GPU, "
                   "dynamic chunk pool (1024 problems per chunk)" % (n_problems, list(batch_runner.NOISE_SWEEP_PX), world, workers),
         "wall_s": wall, "solves_per_s": n_problems / wall,
         "timing": "wall clock from a barrier to the barrier after the last chunk (setup of the resident base arcs excluded); per chunk: "
                   "8-byte seed in, device draws of pixel noise + initial guess, 20 BA iterations, 16 KB of per-problem errors out", "chunks_per_rank": {g[0]: len(g[2]) for g in gathered},
-        "noise_sweep": {str(k): v for k, v in batch_runner.summarize_noise_sweep(allres).items()}}))
+        "noise_sweep": {str(k): v for k, v in batch_runner.summarize_noise_sweep(allres).items()}}) + "\n").encode())
 if world > 1:
     dist.destroy_process_group()
