@@ -543,14 +543,18 @@ int vinsat_satcam_visibility(vinsat_ctx* ctx, const vinsat_satcam_table* table, 
   // host buffers: staged chunk by chunk (bounded device memory); results are gathered on the device and copied once
   const int64_t chunk = 1 << 20;                // 1,048,576 poses = 100 MB per chunk
   const int64_t cn = std::min<int64_t>(chunk, n_poses);
-  DevBuf<double> d_poses, d_ll;
-  DevBuf<uint8_t> d_vis;
-  DevBuf<int32_t> d_cnt, d_reg;
-  VS_CUDA(ctx, d_poses.alloc(cn * 12));
-  VS_CUDA(ctx, d_vis.alloc(n_poses));
-  if (count_out) VS_CUDA(ctx, d_cnt.alloc(n_poses));
-  if (corner_lonlat_out) VS_CUDA(ctx, d_ll.alloc(n_poses * 8));
-  if (corner_region_out) VS_CUDA(ctx, d_reg.alloc(n_poses * 4));
+  // all staging comes from the context's persistent scratch (one allocation that only grows): a sweep called per orbit
+  // must not pay a 100 MB cudaMalloc / cudaFree pair every time
+  const size_t b_poses = (size_t)cn * 12 * sizeof(double);
+  const size_t b_ll = corner_lonlat_out ? (size_t)n_poses * 8 * sizeof(double) : 0;
+  const size_t b_cnt = count_out ? (size_t)n_poses * sizeof(int32_t) : 0;
+  const size_t b_reg = corner_region_out ? (size_t)n_poses * 4 * sizeof(int32_t) : 0;
+  const size_t b_vis = ((size_t)n_poses + 15) & ~(size_t)15;
+  char* sc = (char*)ctx_scratch(ctx, b_poses + b_ll + b_cnt + b_reg + b_vis + 64);
+  if (!sc) return set_error(ctx, VINSAT_ENOMEM, "scratch allocation failed");
+  struct { double* p; } d_poses{(double*)sc}, d_ll{(double*)(sc + b_poses)};
+  struct { int32_t* p; } d_cnt{(int32_t*)(sc + b_poses + b_ll)}, d_reg{(int32_t*)(sc + b_poses + b_ll + b_cnt)};
+  struct { uint8_t* p; } d_vis{(uint8_t*)(sc + b_poses + b_ll + b_cnt + b_reg)};
   int rc = VINSAT_OK;
   for (int64_t p0 = 0; p0 < n_poses && rc == VINSAT_OK; p0 += cn) {
     const int64_t pn = std::min<int64_t>(cn, n_poses - p0);
