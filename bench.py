@@ -275,13 +275,13 @@ def satcam_leg(ctx, rank, world, max_over_ranks, sync_all, fp64_peak, hbm_peak, 
         return {"error": repr(e)[:300]}
 
 
-def longarc_leg(ctx, rank, world, max_over_ranks, sync_all, T=100_000, K=50):
+def longarc_leg(ctx, rank, world, max_over_ranks, sync_all, T=100_000, K=50, make_kw=None):
     """configs[2]: one long arc (T frames x K obs/frame), frame-window sharded over the ranks, 20 BA iterations
     (10 initialize + 10 full) with the NCCL exchanges of vinsat_b200/longarc.py; rank 0 also solves the whole arc alone."""
     import torch
     from vinsat_b200 import _lib, longarc, synth
     try:
-        pr = synth.make_problem(123, T, K, gap_max=3)
+        pr = synth.make_problem(123, T, K, **dict(dict(gap_max=3), **(make_kw or {})))
         ctx._bound_to_torch = True                      # ctx launches on torch's current stream (set by run_gpu)
         la = longarc.LongArc(pr, ctxs=[ctx], use_dist=world > 1, world=world)
         # device-side LM + CUDA graphs (kernels and NCCL captured together) is opt-in: measured on 2 x B200 it is SLOWER than the

@@ -108,3 +108,42 @@ def test_device_side_lm_and_cuda_graphs_equal_host_driven_iterations():
     finally:
         torch.cuda.set_stream(torch.cuda.default_stream())
         ctx.close()
+
+
+@pytest.mark.parametrize("world,nseg", [(1, 40), (2, 25), (3, 17)])
+def test_sharded_arc_with_second_partition_level(ctx, monkeypatch, world, nseg):
+    """With many segments per rank the gathered reduced chain is partitioned a second time (Level2, csrc/batch.h): forced here
+    on a small arc (VINSAT_L2_MIN=16 => ~sqrt(S_total) level-2 segments); the whole-arc reference runs with level 2 off."""
+    pr = synth.make_problem(81, 400, 5)
+    iters = [(0, True), (9, True), (10, False), (11, False), (15, False), (19, False)]
+    monkeypatch.setenv("VINSAT_L2_MIN", "0")
+    ref = _whole(ctx, pr, iters)
+    monkeypatch.setenv("VINSAT_L2_MIN", "16")
+    la = longarc.LongArc(pr, ctxs=[ctx], world=world, n_segments=nseg)
+    lam = 1e-4
+    for k, (it, init) in enumerate(iters):
+        lam, ntr = la.ba_iterate(it, lam, initialize=init)
+        st = la.gather_states()
+        s_ref, lam_ref, ntr_ref = ref[k]
+        assert ntr == ntr_ref and lam == lam_ref, (world, nseg, it)
+        assert np.abs(st[:, :3] - s_ref[:, :3]).max() < 1e-6, (world, nseg, it)
+        assert np.abs(st[:, 7:] - s_ref[:, 7:]).max() < 1e-9, (world, nseg, it)
+        assert np.abs(st[:, 3:7] - s_ref[:, 3:7]).max() < 1e-10, (world, nseg, it)
+    la.close()
+
+
+def test_long_arc_sums_in_two_stages(ctx):
+    """Arcs of more than 4096 frames per problem take the two-stage (chunked) accept sums: same LM schedule and states as the
+    sharded driver (whose sums are chunked per window) and convergence to the truth."""
+    pr = synth.make_problem(82, 9000, 3, gap_max=2)
+    iters = [(it, it < 10) for it in range(20)]
+    ref = _whole(ctx, pr, iters)
+    assert np.abs(ref[-1][0][:, :3] - pr["states_gt"][:, :3]).max() < 2.0
+    la = longarc.LongArc(pr, ctxs=[ctx], world=2)
+    lam = 1e-4
+    for k, (it, init) in enumerate(iters):
+        lam, ntr = la.ba_iterate(it, lam, initialize=init)
+        assert (lam, ntr) == (ref[k][1], ref[k][2]), it
+    st = la.gather_states()
+    assert np.abs(st[:, :3] - ref[-1][0][:, :3]).max() < 1e-5
+    la.close()

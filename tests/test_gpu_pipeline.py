@@ -73,6 +73,42 @@ def test_two_sided_sweep_ragged_lengths(ctx, monkeypatch, lengths, two_sided):
     assert np.all(np.isfinite(st))
 
 
+def test_partitioned_solve_with_second_level_equals_dense_solve(ctx, monkeypatch):
+    """Two-level partition (Level2, csrc/batch.h) forced on small problems: 5-frame level-1 segments, reduced chains of >= 16
+    separators cut again into ~sqrt(S) level-2 segments; problems of 600 / 200 frames take it, 64 / 3 frames ride along with one
+    level-2 segment.  The LM step must solve the same system as a dense LAPACK solve."""
+    monkeypatch.setenv("VINSAT_SEG_LEN", "5")
+    monkeypatch.setenv("VINSAT_L2_MIN", "16")
+    lengths = (600, 200, 64, 3)
+    prs = [synth.make_problem(950 + i, T, 4) for i, T in enumerate(lengths)]
+    b = _lib.Batch(ctx, _lib.concat_problems(prs))
+    lam, ntr = b.ba_iterate(12, 1e-4, initialize=False)
+    dbg = b.debug_fetch()
+    b.close()
+    monkeypatch.setenv("VINSAT_L2_MIN", "0")
+    b = _lib.Batch(ctx, _lib.concat_problems(prs))
+    lam1, ntr1 = b.ba_iterate(12, 1e-4, initialize=False)
+    dbg1 = b.debug_fetch()
+    b.close()
+    assert np.array_equal(ntr, ntr1) and np.array_equal(lam, lam1)
+    fo = np.concatenate([[0], np.cumsum(lengths)])
+    for p, T in enumerate(lengths):
+        D, U, rhs = dbg["D"][fo[p]:fo[p + 1]], dbg["U"][fo[p]:fo[p + 1]], dbg["rhs"][fo[p]:fo[p + 1]]
+        got, one_level = dbg["dpose"][fo[p]:fo[p + 1]].reshape(-1), dbg1["dpose"][fo[p]:fo[p + 1]].reshape(-1)
+        assert np.allclose(got, one_level, rtol=1e-6, atol=1e-9 * np.abs(one_level).max()), (p, np.abs(got - one_level).max())
+        if ntr[p] != 1:
+            continue
+        A = np.zeros((9 * T, 9 * T))
+        for i in range(T):
+            A[9 * i:9 * i + 9, 9 * i:9 * i + 9] = D[i]
+            if i + 1 < T:
+                A[9 * i:9 * i + 9, 9 * i + 9:9 * i + 18] = U[i]
+                A[9 * i + 9:9 * i + 18, 9 * i:9 * i + 9] = U[i].T
+        Al = A + float(np.float32(1e-4)) * np.eye(9 * T)
+        bwd = np.abs(Al @ got - rhs.reshape(-1)).max() / (np.abs(Al).sum(1).max() * np.abs(got).max() + np.abs(rhs).max())
+        assert bwd < 1e-13, (p, T, bwd)
+
+
 def test_device_monte_carlo_draws_and_noise_sweep_pool():
     """mc_perturb: deterministic per seed, right moments; the pooled noise sweep solves every chunk once and errors grow
     with sigma_px."""
@@ -108,3 +144,33 @@ def test_device_monte_carlo_draws_and_noise_sweep_pool():
     assert set(sw) == set(batch_runner.NOISE_SWEEP_PX) and all(v["n"] == 32 for v in sw.values())
     assert sw[0.25]["pos_m_median"] < sw[4.0]["pos_m_median"]
     assert sw[0.25]["pos_m_median"] < 500.0
+
+
+def test_second_device_in_one_process_gets_the_shared_memory_opt_ins():
+    """The > 48 KB dynamic shared-memory opt-ins are per DEVICE; they are tracked per context (csrc/ctx.cu smem_optin).
+    A second context on device 1 of the same process must run the kernels that need them -- k_select_smem with 12,000
+    observations per problem needs (12000 + 2048) * 8 B = 112 KB, the assembly and system kernels opt in as well -- and give
+    bit-identical states.  Needs two GPUs (skipped on the one-GPU test box; run by the builder under `gpurun --gpus 2`)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    arrays = _lib.concat_problems(synth.make_batch(4, 400, 30, seed0=7))
+    outs = []
+    for dev in (0, 1, 0):
+        c = _lib.Context(dev)
+        b = _lib.Batch(c, arrays)
+        b.od_solve(20, 10, 1e-4)
+        outs.append(b.get_states().copy())
+        b.close()
+        c.close()
+    assert np.all(np.isfinite(outs[0]))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    # both devices alive at once, interleaved calls (one host thread)
+    c0, c1 = _lib.Context(0), _lib.Context(1)
+    b0, b1 = _lib.Batch(c0, arrays), _lib.Batch(c1, arrays)
+    for it in range(3):
+        b0.ba_iterate(it, 1e-4, initialize=True)
+        b1.ba_iterate(it, 1e-4, initialize=True)
+    assert np.array_equal(b0.get_states(), b1.get_states())
+    for x in (b0, b1, c0, c1):
+        x.close()

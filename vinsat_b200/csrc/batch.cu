@@ -44,11 +44,17 @@ void free_all(vinsat_batch* b) {
                   b->seg_left, b->seg_prob, b->seg_has_next, b->pl_a, b->pl_b, b->pl_prob, b->red_a, b->red_b,
                   b->bb_a, b->bb_e, b->bb_dir, b->bb_prob, b->bb_mid, b->midrec,
                   b->redrec, b->rsys, b->rlow, b->rwrec, b->la_pack, b->la_gath, b->la_rsys, b->la_rlow, b->la_rwrec,
-                  b->la_xsep, b->la_sums, b->la_edge, b->la_edges_all, b->la_chain};
+                  b->la_xsep, b->la_sums, b->la_edge, b->la_edges_all, b->la_chain, b->sum_part, b->sum_chunk_off,
+                  b->l2.a, b->l2.b, b->l2.left, b->l2.prob, b->l2.has_next, b->l2.red_a, b->l2.red_b, b->l2.red_prob,
+                  b->l2.redrec, b->l2.rsys, b->l2.rlow, b->l2.rwrec, b->xsep};
   if (!b->in_arena)
     for (void* p : ptrs)
       if (p) cudaFree(p);
   if (b->J) cudaFree(b->J);
+  for (void* p : {(void*)b->la_l2.a, (void*)b->la_l2.b, (void*)b->la_l2.left, (void*)b->la_l2.prob, (void*)b->la_l2.has_next,
+                  (void*)b->la_l2.red_a, (void*)b->la_l2.red_b, (void*)b->la_l2.red_prob, (void*)b->la_l2.redrec,
+                  (void*)b->la_l2.rsys, (void*)b->la_l2.rlow, (void*)b->la_l2.rwrec})
+    if (p) cudaFree(p);            // vinsat_la_alloc_reduced: plain cudaMalloc
   for (void* p : {(void*)b->mc_st_true, (void*)b->mc_uv_true, (void*)b->mc_vel_true, (void*)b->mc_err, (void*)b->pr_st,
                   (void*)b->pr_Hs, (void*)b->pr_Hr, (void*)b->e_pr_init, (void*)b->e_pr})
     if (p) cudaFree(p);            // allocated lazily with cudaMalloc, never from the arena
@@ -115,6 +121,7 @@ int build_frame_index(vinsat_batch* b, const vinsat_problem_desc* d, std::vector
 struct Segmentation {
   std::vector<int32_t> a, b, left, prob, has_next, pl_a, pl_b, pl_prob, red_a, red_b;
   std::vector<int32_t> bb_a, bb_e, bb_dir, bb_prob, bb_mid;
+  Level2Host l2;
   bool partitioned = false;
 };
 
@@ -159,6 +166,14 @@ Segmentation make_segments(const vinsat_ctx* ctx, int64_t P, const int64_t* fram
       else {
         S = (int64_t)llround((double)Tp * target_chains / (double)std::max<int64_t>(T, 1));
         S = std::min<int64_t>(S, (int64_t)sqrt((double)Tp));
+        // long problems: as many segments as the GPU runs chains at once (8 one-warp CTAs x 3 chains per SM), each at least
+        // 24 frames long; the reduced chain over them is then partitioned a second time (Level2) instead of being walked by
+        // one warp.  Sequential depth of a 2.4 M-frame arc: 676 + 60 + 60 eliminations instead of 1549 + 1549.
+        {
+          const double one_wave = 8.0 * ctx->sm_count * 3;
+          const int64_t S2 = std::min<int64_t>((int64_t)llround((double)Tp * one_wave / (double)std::max<int64_t>(T, 1)), Tp / 24);
+          if (S2 >= level2_min_separators() && S2 > S) S = S2;
+        }
         if (Tp < 64) S = 1;
         // measured on B200 (T=1000, two-sided fused sweep vs partitioned sweep + materialised system): 14.7 k solves/s
         // either way at P = 256, 21.2 k vs 16.3 k at P = 512, 9.3 k vs 11.8 k at P = 128 => partition below ~1.75
@@ -178,6 +193,7 @@ Segmentation make_segments(const vinsat_ctx* ctx, int64_t P, const int64_t* fram
     }
     s.red_b.push_back((int32_t)s.a.size());
   }
+  if (s.partitioned) s.l2 = plan_level2(s.red_a, s.red_b, s.pl_prob, level2_min_separators());
   return s;
 }
 
@@ -205,6 +221,11 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
   VS_TRY(build_frame_index(b, d, gap, fprob, order));
   VS_CUDA(ctx, cudaMemcpyAsync(b->d_frame_off, d->frame_off, (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
   VS_CUDA(ctx, cudaMemcpyAsync(b->d_obs_off, d->obs_off, (P + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  std::vector<int32_t> chunk_off(P + 1, 0);
+  for (int64_t p = 0; p < P; p++)
+    chunk_off[p + 1] = chunk_off[p] + (int32_t)ceil_div(d->frame_off[p + 1] - d->frame_off[p], kSumChunk);
+  b->sum_chunks = chunk_off[P];
+  VS_CUDA(ctx, cudaMemcpyAsync(b->sum_chunk_off, chunk_off.data(), (P + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   VS_CUDA(ctx, cudaMemcpyAsync(b->gap, gap.data(), T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   VS_CUDA(ctx, cudaMemcpyAsync(b->fprob, fprob.data(), T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   if (b->n_pairs)
@@ -214,7 +235,7 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
   VS_CUDA(ctx, cudaMemcpyAsync(b->crot, d->cum_rot, T * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
   {
     Segmentation sg = make_segments(ctx, P, d->frame_off, b);
-    if ((int64_t)sg.a.size() != b->n_seg)
+    if ((int64_t)sg.a.size() != b->n_seg || (int64_t)sg.l2.a.size() != b->l2.n || (int64_t)sg.l2.red_a.size() != b->l2.n_chains)
       return set_error(ctx, VINSAT_EINVAL, "vinsat_batch_upload: segmentation differs (frame_off must not change)");
     b->partitioned = sg.partitioned;
     auto up = [&](int32_t* dst, const std::vector<int32_t>& v) {
@@ -226,6 +247,12 @@ int do_upload(vinsat_batch* b, const vinsat_problem_desc* d) {
     VS_CUDA(ctx, up(b->red_a, sg.red_a)); VS_CUDA(ctx, up(b->red_b, sg.red_b));
     VS_CUDA(ctx, up(b->bb_a, sg.bb_a)); VS_CUDA(ctx, up(b->bb_e, sg.bb_e)); VS_CUDA(ctx, up(b->bb_dir, sg.bb_dir));
     VS_CUDA(ctx, up(b->bb_prob, sg.bb_prob)); VS_CUDA(ctx, up(b->bb_mid, sg.bb_mid));
+    if (b->l2.n > 0) {
+      VS_CUDA(ctx, up(b->l2.a, sg.l2.a)); VS_CUDA(ctx, up(b->l2.b, sg.l2.b)); VS_CUDA(ctx, up(b->l2.left, sg.l2.left));
+      VS_CUDA(ctx, up(b->l2.prob, sg.l2.prob)); VS_CUDA(ctx, up(b->l2.has_next, sg.l2.has_next));
+      VS_CUDA(ctx, up(b->l2.red_a, sg.l2.red_a)); VS_CUDA(ctx, up(b->l2.red_b, sg.l2.red_b));
+      VS_CUDA(ctx, up(b->l2.red_prob, sg.l2.red_prob));
+    }
     VS_CUDA(ctx, cudaStreamSynchronize(s));     // the host vectors die at the end of this scope
   }
   VS_CUDA(ctx, cudaMemsetAsync(b->flags, 0, 4 * sizeof(int32_t), s));
@@ -284,14 +311,25 @@ static int create_impl(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t ow
   b->T = d->frame_off[b->P];
   b->M = d->obs_off[b->P];
   const int64_t P = b->P, T = b->T, M = b->M;
-  b->n_seg = (int64_t)make_segments(ctx, P, d->frame_off, b).a.size();
-  const int64_t NS = b->n_seg;
+  {
+    const Segmentation sg0 = make_segments(ctx, P, d->frame_off, b);
+    b->n_seg = (int64_t)sg0.a.size();
+    b->l2.n = (int64_t)sg0.l2.a.size();
+    b->l2.n_chains = (int64_t)sg0.l2.red_a.size();
+  }
+  const int64_t NS = b->n_seg, N2 = b->l2.n, C2 = b->l2.n_chains;
   int rc = VINSAT_OK;
 #define A(ptr, n) if (rc == VINSAT_OK) rc = dev_alloc(ctx, &b->ptr, (n))
   A(seg_a, NS); A(seg_b, NS); A(seg_left, NS); A(seg_prob, NS); A(seg_has_next, NS);
   A(pl_a, P); A(pl_b, P); A(pl_prob, P); A(red_a, P); A(red_b, P);
   A(bb_a, 2 * P); A(bb_e, 2 * P); A(bb_dir, 2 * P); A(bb_prob, 2 * P); A(bb_mid, 2 * P); A(midrec, 2 * P * 96);
   A(redrec, NS * VS_RREC); A(rsys, NS * VS_SREC); A(rlow, NS * 81); A(rwrec, NS * VS_WREC);
+  if (N2 > 0) {
+    A(l2.a, N2); A(l2.b, N2); A(l2.left, N2); A(l2.prob, N2); A(l2.has_next, N2);
+    A(l2.red_a, C2); A(l2.red_b, C2); A(l2.red_prob, C2);
+    A(l2.redrec, N2 * VS_RREC); A(l2.rsys, N2 * VS_SREC); A(l2.rlow, N2 * 81); A(l2.rwrec, N2 * VS_WREC);
+    A(xsep, NS * 9);
+  }
   if (b->window) { A(la_pack, NS * (VS_RREC + VS_SREC)); A(la_sums, 4); A(la_edge, 20); }
   A(st, T * 10); A(st_new, T * 10); A(intr, T * 4); A(crot, T * 4); A(gap, T); A(fprob, T); A(dyn_order, T);
   A(obs_start, T + 1); A(grec, T * VS_GREC); A(drec, T * VS_DREC); A(mrec, T * VS_MREC); A(srec, T * VS_SREC); A(wrec, T * VS_WREC);
@@ -299,6 +337,8 @@ static int create_impl(vinsat_ctx* ctx, const vinsat_problem_desc* d, int64_t ow
   A(X, M * 3); A(uv, M * 2); A(conf, M); A(oframe, M); A(r, M * 2); A(r_next, M * 2); A(wu, M);
   A(d_frame_off, P + 1); A(d_obs_off, P + 1); A(c_obs, P); A(wmax, P); A(lam, P); A(lam_next, P); A(lam32_last, P);
   A(init_res, P); A(active, P); A(ntrials, P); A(sel_prefix, P); A(sel_rank, P); A(sel_hist, P * 2048); A(flags, 4);
+  b->sum_chunks_cap = T / kSumChunk + P + 1;
+  A(sum_part, b->sum_chunks_cap * 3); A(sum_chunk_off, P + 1);
 #undef A
   if (rc == VINSAT_OK && cudaMallocHost((void**)&b->h_flags, 4 * sizeof(int32_t)) != cudaSuccess) {
     cudaGetLastError();

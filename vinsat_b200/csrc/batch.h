@@ -1,6 +1,9 @@
 // Device-resident batch of OD problems (internal).
 #pragma once
+#include <cmath>
+#include <cstdlib>
 #include <map>
+#include <vector>
 #include <set>
 #include "internal.h"
 
@@ -10,7 +13,56 @@
 #define VS_MREC 42    // Phi^T D^2 Phi (6x6, both triangles, [a*6+b]) | Phi^T D r (6)  (written by k_dynamics_stm)
 #define VS_SREC 172   // system: D 81 | U 81 | b 9 | pad 1
 #define VS_WREC 172   // solver: W = S^-1 U (col-major 81) | y 9 | Z spike (col-major 81) | pad
+constexpr int kSumChunk = 2048;     // frames per CTA of the two-stage per-problem sums (long arcs, kernels_solve.cu)
+constexpr int kSumThreads = 256;
 #define VS_RREC 342   // reduced-system contributions of a segment: left {Dl 81, Ll 81, bl 9} | right {Dr 81, Ur 81, br 9}
+
+// Second partition level of the block-tridiagonal solve (kernels_chain.cu): the REDUCED chain of a long problem (one element
+// per level-1 separator) is itself cut into segments, so that the sequential depth of a solve is
+// len(level-1 segment) + len(level-2 segment) + #level-2 segments instead of len + #level-1 segments.
+// Indices a / b / left are level-1 separator numbers.
+struct Level2 {
+  int64_t n = 0;            // level-2 segments (0 = off)
+  int64_t n_chains = 0;     // reduced-2 chains (one per problem)
+  int32_t *a = nullptr, *b = nullptr, *left = nullptr, *prob = nullptr, *has_next = nullptr;   // [n]
+  int32_t *red_a = nullptr, *red_b = nullptr, *red_prob = nullptr;                            // [n_chains]
+  double *redrec = nullptr, *rsys = nullptr, *rlow = nullptr, *rwrec = nullptr;               // [n] records
+};
+
+struct Level2Host {
+  std::vector<int32_t> a, b, left, prob, has_next, red_a, red_b, red_prob;
+};
+
+// Plan: problems whose reduced chain has >= min_sep elements get ~sqrt(S) level-2 segments, the others one.
+// Empty (no level 2) when no problem is that long.
+inline Level2Host plan_level2(const std::vector<int32_t>& red_a, const std::vector<int32_t>& red_b,
+                              const std::vector<int32_t>& prob, int64_t min_sep) {
+  Level2Host h;
+  bool any = false;
+  for (size_t p = 0; p < red_a.size(); p++) any = any || (red_b[p] - red_a[p] >= min_sep);
+  if (!any) return h;
+  for (size_t p = 0; p < red_a.size(); p++) {
+    const int64_t S = red_b[p] - red_a[p];
+    const int64_t S2 = S >= min_sep ? std::max<int64_t>(2, llround(sqrt((double)S))) : (S > 0 ? 1 : 0);
+    h.red_a.push_back((int32_t)h.a.size());
+    for (int64_t k = 0; k < S2; k++) {
+      const int64_t lo = red_a[p] + (S * k) / S2, hi = red_a[p] + (S * (k + 1)) / S2;   // elements [lo, hi), separator hi-1
+      h.a.push_back((int32_t)lo);
+      h.b.push_back((int32_t)(hi - 1));
+      h.left.push_back(k > 0 ? (int32_t)(lo - 1) : -1);
+      h.prob.push_back(prob[p]);
+      h.has_next.push_back(k + 1 < S2 ? 1 : 0);
+    }
+    h.red_b.push_back((int32_t)h.a.size());
+    h.red_prob.push_back(prob[p]);
+  }
+  return h;
+}
+
+inline int64_t level2_min_separators() {
+  const int64_t v = getenv("VINSAT_L2_MIN") ? atoll(getenv("VINSAT_L2_MIN")) : 256;    // <= 0: level 2 off (read at batch creation)
+  return v > 0 ? v : (int64_t)1 << 62;
+}
 
 struct vinsat_batch {
   vinsat_ctx* ctx = nullptr;
@@ -48,6 +100,8 @@ struct vinsat_batch {
   double* rsys = nullptr;      // [n_seg][VS_SREC] reduced system rows
   double* rlow = nullptr;      // [n_seg][81] explicit lower blocks of the reduced system
   double* rwrec = nullptr;     // [n_seg][VS_WREC]
+  Level2 l2;                   // second partition level over the reduced chains (long problems)
+  double* xsep = nullptr;      // [n_seg][9] level-1 separator solutions (level-2 path)
   double* e_obs = nullptr;     // [T] trial partial sums (obs part)
   double* e_dyn = nullptr;     // [T] trial partial sums (dynamics part)
   // ---- device, per observation (SoA) ----
@@ -98,9 +152,14 @@ struct vinsat_batch {
   double* la_rwrec = nullptr;         // [S_total][VS_WREC]
   double* la_xsep = nullptr;          // [S_total][9]
   double* la_sums = nullptr;          // [4]
+  // two-stage per-problem sums of long arcs (k_sum_partials)
+  double* sum_part = nullptr;         // [sum_chunks_cap][3]
+  int32_t* sum_chunk_off = nullptr;   // [P+1] first chunk of every problem
+  int64_t sum_chunks = 0, sum_chunks_cap = 0;
   double* la_edge = nullptr;          // [2][10] new states of the first / last owned frame
   double* la_edges_all = nullptr;     // [n_ranks][2][10]
   int32_t* la_chain = nullptr;        // {0, S_total, 0}
+  Level2 la_l2;                       // second partition level over the gathered reduced chain
   // ---- Monte-Carlo noise sweeps (mc.cu): true states / pixels the perturbations are drawn around, error scratch ----
   double *mc_st_true = nullptr, *mc_uv_true = nullptr, *mc_vel_true = nullptr, *mc_err = nullptr;
   // ---- BA_reg (prior.cu): prior states / information matrices and the per-frame sums of |r_prior| ----

@@ -750,7 +750,14 @@ __global__ void __launch_bounds__(128) k_chain_backward(ChainArgs A) {
 // and the RIGHT part of the left separator's row: Dr = -U_left Zh_a, Ur = -U_left Wh_a, br = -U_left yh_a.
 // Lanes 0-8 own Wh columns, lane 9 owns yh, lanes 10-18 own Zh columns.
 // ---------------------------------------------------------------------------------------------------------
+// The records are streamed through a shared-memory ring with cp.async, kBrRing elements ahead (a step is ~600 cycles of
+// work, an HBM round trip ~1000: loading each record when it is needed made this pass slower than the elimination itself,
+// 2.9 ms against 2.1 ms on a 2.4 M-frame arc).
+constexpr int kBrRing = 4;
+constexpr int kBrRow = 184;     // W re-strided to 9 x kMS (90) | y (9) at 90 | Z col-major (81) at 99 | pad
+
 __global__ void __launch_bounds__(128) k_seg_backrec(ChainArgs A) {
+  __shared__ __align__(16) double s_ring[4][kBrRing][kBrRow];
   __shared__ __align__(16) double s_M[4][9 * kMS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x * 4 + warp;
@@ -767,11 +774,26 @@ __global__ void __launch_bounds__(128) k_seg_backrec(ChainArgs A) {
     for (int idx = lane; idx < 171; idx += 32) rq[idx] = (idx >= 81 && idx < 162) ? Ul[idx - 81] : 0.0;
     return;
   }
+  double (*ring)[kBrRow] = s_ring[warp];
+  auto issue = [&](int i, int slot) {          // wrec of interior element i -> ring[slot]
+    if (i >= a) {
+      const double* w = A.wrec + (int64_t)i * VS_WREC;
+      double* dst = ring[slot];
+      for (int idx = lane; idx < 171; idx += 32) {
+        const int d = idx < 81 ? (idx / 9) * kMS + (idx % 9) : idx + 9;
+        __pipeline_memcpy_async(dst + d, w + idx, 8);
+      }
+    }
+    __pipeline_commit();
+  };
+#pragma unroll
+  for (int d = 0; d < kBrRing; d++) issue(e - 2 - d, d);
   double* M = s_M[warp];
   const bool isW = lane < 9, isY = lane == 9, isZ = lane >= 10 && lane < 19;
   const int cc = isW ? lane : (isZ ? lane - 10 : 0);
   // own column of element i inside a wrec record: W col cc | y | Z col cc
   const int off = isW ? cc * 9 : (isY ? 81 : 90 + cc * 9);
+  const int roff = isY ? 90 : 99 + cc * 9;             // the same column inside a ring slot (y / Z only)
   const bool act = lane < 19;
   double h[9], own[9];
   {
@@ -779,18 +801,20 @@ __global__ void __launch_bounds__(128) k_seg_backrec(ChainArgs A) {
 #pragma unroll
     for (int r = 0; r < 9; r++) h[r] = act ? w[off + r] : 0.0;
   }
+  int slot = 0;
   for (int i = e - 2; i >= a; i--) {
-    const double* w = A.wrec + (int64_t)i * VS_WREC;
-    // stage W_i: M[c*kMS + r] = W_i[r][c]  (stored col-major at w[c*9 + r])
-    for (int idx = lane; idx < 81; idx += 32) M[(idx / 9) * kMS + (idx % 9)] = w[idx];
-#pragma unroll
-    for (int r = 0; r < 9; r++) own[r] = (act && !isW) ? w[off + r] : 0.0;
+    __pipeline_wait_prior(kBrRing - 1);
     __syncwarp();
+    const double* R = ring[slot];              // R[c*kMS + r] = W_i[r][c]
+#pragma unroll
+    for (int r = 0; r < 9; r++) own[r] = (act && !isW) ? R[roff + r] : 0.0;
     double o[9];
-    matvec9(M, h, o);
+    matvec9(R, h, o);
 #pragma unroll
     for (int r = 0; r < 9; r++) h[r] = own[r] - o[r];
     __syncwarp();
+    issue(i - kBrRing, slot);
+    slot = (slot + 1 == kBrRing) ? 0 : slot + 1;
   }
   // M[k*kMS + r] = U_left[r][k]
   for (int idx = lane; idx < 81; idx += 32) { const int r = idx / 9, k = idx % 9; M[k * kMS + r] = Ul[idx]; }
@@ -831,7 +855,7 @@ __global__ void __launch_bounds__(256) k_reduced_build(int n_seg, const int32_t*
   double v;
   if (e < 81) {
     v = fr[e] + mine[e] + (nx ? next[e] : 0.0);
-    if (e / 9 == e % 9) v += (double)(float)lam[prob];
+    if (lam && e / 9 == e % 9) v += (double)(float)lam[prob];        // lam == null: level 2 (already damped at level 1)
   } else if (e < 162) {
     v = nx ? next[e] : 0.0;
   } else {
@@ -852,6 +876,7 @@ __global__ void __launch_bounds__(128) k_seg_backsub(int n_chains, const int32_t
                                                      const int32_t* __restrict__ ch_prob,
                                                      const int32_t* __restrict__ active,
                                                      const double* __restrict__ wrec, double* __restrict__ delta) {
+  constexpr int kRing = 4;       // (shadows the 8 of k_chain_backward) 22.5 KB per CTA: every CTA of a 3552-segment arc resident
   __shared__ __align__(16) double s_ring[4][kRing][176];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x * 4 + warp;
@@ -958,11 +983,62 @@ int launch_seg_backsub(vinsat_batch* b) {
   return VINSAT_OK;
 }
 
+// separator solutions -> rows of the frames they belong to
+__global__ void __launch_bounds__(128) k_sep_scatter(int n_seg, const int32_t* __restrict__ seg_b,
+                                                     const int32_t* __restrict__ seg_prob, const int32_t* __restrict__ active,
+                                                     const double* __restrict__ xsep, double* __restrict__ delta) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int s = (int)(t / 9), r = (int)(t % 9);
+  if (s >= n_seg) return;
+  if (active && !active[seg_prob[s]]) return;
+  delta[(int64_t)seg_b[s] * 9 + r] = xsep[t];
+}
+
+// Second partition level: solves the reduced chains {rsys | rlow} (one element per level-1 separator, explicit lower blocks,
+// already damped) by the same partitioned algorithm -- spike elimination of the level-2 interiors, backward recurrence,
+// a (short) reduced-2 chain per problem, interior back-substitution -- and leaves the level-1 separator solutions in xsep.
+int launch_level2_solve(vinsat_ctx* ctx, const Level2& L, const int32_t* active, const double* rsys, const double* rlow,
+                        double* rwrec, double* xsep) {
+  ChainArgs A;
+  A.n_chains = (int)L.n;
+  A.ch_a = L.a; A.ch_b = L.b; A.ch_left = L.left; A.ch_prob = L.prob;
+  A.active = active;
+  A.lam = nullptr;
+  A.rec = rsys;
+  A.lrec = rlow;
+  A.wrec = rwrec;
+  A.redrec = L.redrec;
+  A.delta = xsep;
+  A.out_index = nullptr;
+  A.lam32_last = nullptr;
+  VS_TRY(launch_forward<true>(ctx, A));
+  VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
+  VS_LAUNCH(ctx, F_SOLVE, k_reduced_build, ceil_div(L.n * 192, 256), 256, 0, (int)L.n, L.b, L.left, L.prob, L.has_next, active,
+            (const double*)nullptr, rsys, L.redrec, L.rsys, L.rlow);
+  ChainArgs R;
+  R.n_chains = (int)L.n_chains;
+  R.ch_a = L.red_a; R.ch_b = L.red_b; R.ch_left = nullptr; R.ch_prob = L.red_prob;
+  R.active = active;
+  R.lam = nullptr;
+  R.rec = L.rsys;
+  R.lrec = L.rlow;
+  R.wrec = L.rwrec;
+  R.redrec = nullptr;
+  R.delta = xsep;
+  R.out_index = L.b;               // level-2 separator -> level-1 separator it is
+  R.lam32_last = nullptr;
+  VS_TRY(launch_forward<false>(ctx, R));
+  VS_LAUNCH(ctx, F_SOLVE, k_chain_backward, ceil_div(R.n_chains, 4), 128, 0, R);
+  VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div(L.n, 4), 128, 0, (int)L.n, L.a, L.b, L.left, L.prob, active, rwrec, xsep);
+  return VINSAT_OK;
+}
+
 int launch_reduced_packed(vinsat_batch* b, int64_t S_total, const double* pack, double* rsys, double* rlow,
                           double* rwrec, double* xsep, const int32_t* one_chain) {
   vinsat_ctx* ctx = b->ctx;
   VS_LAUNCH(ctx, F_SOLVE, k_reduced_build_packed, ceil_div(S_total * 192, 256), 256, 0, (int)S_total, pack, b->lam, rsys,
             rlow);
+  if (b->la_l2.n > 0) return launch_level2_solve(ctx, b->la_l2, nullptr, rsys, rlow, rwrec, xsep);
   ChainArgs R;
   R.n_chains = 1;
   R.ch_a = one_chain; R.ch_b = one_chain + 1; R.ch_left = nullptr; R.ch_prob = one_chain + 2;
@@ -1021,6 +1097,14 @@ int launch_chain_solve(vinsat_batch* b) {
   VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
   VS_LAUNCH(ctx, F_SOLVE, k_reduced_build, ceil_div((int64_t)b->n_seg * 192, 256), 256, 0, (int)b->n_seg, b->seg_b,
             b->seg_left, b->seg_prob, b->seg_has_next, b->active, b->lam, b->srec, b->redrec, b->rsys, b->rlow);
+  if (b->l2.n > 0) {
+    VS_TRY(launch_level2_solve(ctx, b->l2, b->active, b->rsys, b->rlow, b->rwrec, b->xsep));
+    VS_LAUNCH(ctx, F_SOLVE, k_sep_scatter, ceil_div(b->n_seg * 9, 128), 128, 0, (int)b->n_seg, b->seg_b, b->seg_prob, b->active,
+              b->xsep, b->delta);
+    VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div((int64_t)b->n_seg, 4), 128, 0, (int)b->n_seg, b->seg_a, b->seg_b,
+              b->seg_left, b->seg_prob, b->active, b->wrec, b->delta);
+    return VINSAT_OK;
+  }
   ChainArgs R;
   R.n_chains = (int)b->P;
   R.ch_a = b->red_a; R.ch_b = b->red_b; R.ch_left = nullptr; R.ch_prob = b->pl_prob;

@@ -450,7 +450,79 @@ __device__ __forceinline__ double group_total(double v, double* s_part) {
   return t;
 }
 
+// Long arcs (few problems, millions of frames each): a per-problem sum by ONE CTA is a latency-bound walk (5 ms for 2.4 M
+// frames).  Two stages instead: stage 1 sums fixed chunks of kSumChunk frames, one CTA each, into part[chunk][3]; stage 2
+// (k_init_residual / k_accept below, or k_la_sums_final of the sharded arc) adds a problem's chunk sums.  Chunk c of problem
+// p covers frames [frame_off[p] + (c - chunk_off[p]) * kSumChunk, ...) -- fixed shapes, fixed order => still deterministic.
+//   MODE 0: linearisation sums  { sum grec[f][27], sum_{pairs} |r_pred| (7 components), sum e_prior }
+//   MODE 1: trial sums          { sum e_obs[f],    sum_{pairs} e_dyn[f],                sum e_prior }
+// `lo`/`hi` (hi > lo) restrict the sums to the OWNED frames of a window batch (one problem).
+template <int MODE>
+__global__ void __launch_bounds__(kSumThreads) k_sum_partials(int P, const int32_t* __restrict__ chunk_off,
+                                                              const int64_t* __restrict__ frame_off, int64_t lo, int64_t hi,
+                                                              const int32_t* __restrict__ gap,
+                                                              const double* __restrict__ grec,
+                                                              const double* __restrict__ drec,
+                                                              const double* __restrict__ e_obs,
+                                                              const double* __restrict__ e_dyn,
+                                                              const double* __restrict__ e_prior, int initialize,
+                                                              const int32_t* __restrict__ gate, double* __restrict__ part) {
+  if (gate && *gate) return;
+  __shared__ double s_part[3][kSumThreads / 32];
+  const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int p = 0;
+  {                                       // problem of the chunk: last p with chunk_off[p] <= c
+    int a = 0, b = P;
+    while (b - a > 1) { const int m = (a + b) >> 1; if (chunk_off[m] <= c) a = m; else b = m; }
+    p = a;
+  }
+  const int64_t pf1 = frame_off[p + 1];
+  int64_t f0 = frame_off[p], f1 = pf1;
+  const bool window = hi > lo;
+  if (window) { f0 = lo; f1 = hi; }
+  const int64_t c0 = f0 + (int64_t)(c - chunk_off[p]) * kSumChunk, c1 = min(c0 + kSumChunk, f1);
+  double so = 0.0, sd = 0.0, sp = 0.0;
+  for (int64_t f = c0 + tid; f < c1; f += kSumThreads) {
+    if (e_prior) sp += e_prior[f];
+    // same pair rule as the one-stage kernels this replaces (k_accept: f + 1 < f1; the others: gap[f] > 0)
+    const bool pair = !initialize && ((MODE == 1 && !window) ? (f + 1 < pf1) : (gap[f] > 0));
+    if (MODE == 0) {
+      so += grec[f * VS_GREC + 27];
+      if (pair) {
+        const double* d = drec + f * VS_DREC + 36;
+        sd += fabs(d[0]) + fabs(d[1]) + fabs(d[2]) + fabs(d[3]) + fabs(d[4]) + fabs(d[5]) + fabs(d[6]);
+      }
+    } else {
+      so += e_obs[f];
+      if (pair) sd += e_dyn[f];
+    }
+  }
+  so = warp_sum(so); sd = warp_sum(sd); sp = warp_sum(sp);
+  if (lane == 0) { s_part[0][warp] = so; s_part[1][warp] = sd; s_part[2][warp] = sp; }
+  __syncthreads();
+  if (tid < 3) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kSumThreads / 32; w++) t += s_part[tid][w];
+    part[(int64_t)c * 3 + tid] = t;
+  }
+}
+
+int launch_sum_partials(vinsat_batch* b, int mode, int initialize, const double* e_prior, int64_t lo, int64_t hi) {
+  vinsat_ctx* ctx = b->ctx;
+  const unsigned n = (unsigned)((hi > lo) ? ceil_div(hi - lo, kSumChunk) : b->sum_chunks);
+  if (n == 0) return VINSAT_OK;
+  if (mode == 0)
+    VS_LAUNCH(ctx, F_ACCEPT, k_sum_partials<0>, n, kSumThreads, 0, (int)b->P, b->sum_chunk_off, b->d_frame_off, lo, hi, b->gap,
+              b->grec, b->drec, b->e_obs, b->e_dyn, e_prior, initialize, b->gate_arg, b->sum_part);
+  else
+    VS_LAUNCH(ctx, F_ACCEPT, k_sum_partials<1>, n, kSumThreads, 0, (int)b->P, b->sum_chunk_off, b->d_frame_off, lo, hi, b->gap,
+              b->grec, b->drec, b->e_obs, b->e_dyn, e_prior, initialize, b->gate_arg, b->sum_part);
+  return VINSAT_OK;
+}
+
 // init_residual = mean |[r_obs ; sqrt(Sigma) r_pred]| (BA_filtering.py:51); also arms the LM loop.
+// `part` != null: the sums come from the chunk sums of k_sum_partials (long arcs).
 template <int kPT>
 __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_init_residual(int P, const int64_t* __restrict__ frame_off,
                                                        const int64_t* __restrict__ obs_off,
@@ -461,7 +533,9 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_init_residual(int P, 
                                                        double* __restrict__ lam, double* __restrict__ init_res,
                                                        int32_t* __restrict__ active, int32_t* __restrict__ ntrials,
                                                        const int32_t* __restrict__ gate,
-                                                       const double* __restrict__ e_prior) {
+                                                       const double* __restrict__ e_prior,
+                                                       const double* __restrict__ part,
+                                                       const int32_t* __restrict__ chunk_off) {
   if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   __shared__ double s_part[32];
   const int p = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kPT);
@@ -469,6 +543,11 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_init_residual(int P, 
   if (p >= P) return;                    // whole groups leave together (kPT divides blockDim.x)
   const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
   double so = 0.0, sd = 0.0, sp = 0.0;
+  if (part) {
+    for (int c = chunk_off[p] + lane; c < chunk_off[p + 1]; c += kPT) {
+      so += part[(int64_t)c * 3]; sd += part[(int64_t)c * 3 + 1]; sp += part[(int64_t)c * 3 + 2];
+    }
+  } else
   for (int64_t f = f0 + lane; f < f1; f += kPT) {
     if (e_prior) sp += e_prior[f];        // BA_reg: r_prior enters unscaled, 7 components per frame (BA_filtering.py:163)
     so += grec[f * VS_GREC + 27];
@@ -493,14 +572,15 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_init_residual(int P, 
 int launch_init_residual(vinsat_batch* b, int initialize, double Sigma, double, const double* d_lam_in, const double* e_prior) {
   vinsat_ctx* ctx = b->ctx;
   if (b->P == 0) return VINSAT_OK;
-  if (b->T > 4096 * b->P) {              // long arcs: one CTA per problem
+  if (b->T > 4096 * b->P) {              // long arcs: chunk sums by many CTAs, then one CTA per problem adds them
+    if (int rc = launch_sum_partials(b, 0, initialize, e_prior, 0, 0)) return rc;
     VS_LAUNCH(ctx, F_ACCEPT, k_init_residual<1024>, (unsigned)b->P, 1024, 0, (int)b->P, b->d_frame_off,
               b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
-              b->active, b->ntrials, b->gate_arg, e_prior);
+              b->active, b->ntrials, b->gate_arg, e_prior, b->sum_part, b->sum_chunk_off);
   } else {
     VS_LAUNCH(ctx, F_ACCEPT, k_init_residual<32>, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off,
               b->d_obs_off, b->gap, b->grec, b->drec, initialize, sqrt(Sigma), d_lam_in, b->lam, b->init_res,
-              b->active, b->ntrials, b->gate_arg, e_prior);
+              b->active, b->ntrials, b->gate_arg, e_prior, nullptr, nullptr);
   }
   return VINSAT_OK;
 }
@@ -515,7 +595,8 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_accept(int P, const i
                                                 const double* __restrict__ init_res, double* __restrict__ lam,
                                                 double* __restrict__ lam_next, int32_t* __restrict__ active,
                                                 int32_t* __restrict__ ntrials, int32_t* __restrict__ flags,
-                                                const int32_t* __restrict__ gate, const double* __restrict__ e_prior) {
+                                                const int32_t* __restrict__ gate, const double* __restrict__ e_prior,
+                                                const double* __restrict__ part, const int32_t* __restrict__ chunk_off) {
   if (gate && *gate) return;      // speculative launch behind an LM loop that is not finished (batch.cu)
   __shared__ double s_part[32];
   const int p = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kPT);
@@ -524,6 +605,11 @@ __global__ void __launch_bounds__(kPT == 32 ? 128 : kPT) k_accept(int P, const i
   if (!active[p]) return;                // uniform over the group
   const int64_t f0 = frame_off[p], f1 = frame_off[p + 1];
   double so = 0.0, sd = 0.0, sp = 0.0;
+  if (part) {
+    for (int c = chunk_off[p] + lane; c < chunk_off[p + 1]; c += kPT) {
+      so += part[(int64_t)c * 3]; sd += part[(int64_t)c * 3 + 1]; sp += part[(int64_t)c * 3 + 2];
+    }
+  } else
   for (int64_t f = f0 + lane; f < f1; f += kPT) {
     if (e_prior) sp += e_prior[f];
     so += e_obs[f];
@@ -555,13 +641,14 @@ int launch_accept(vinsat_batch* b, int initialize, double Sigma, const double* e
   vinsat_ctx* ctx = b->ctx;
   if (b->P == 0) return VINSAT_OK;
   if (b->T > 4096 * b->P) {
+    if (int rc = launch_sum_partials(b, 1, initialize, e_prior, 0, 0)) return rc;
     VS_LAUNCH(ctx, F_ACCEPT, k_accept<1024>, (unsigned)b->P, 1024, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
               b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
-              b->ntrials, b->flags, b->gate_arg, e_prior);
+              b->ntrials, b->flags, b->gate_arg, e_prior, b->sum_part, b->sum_chunk_off);
   } else {
     VS_LAUNCH(ctx, F_ACCEPT, k_accept<32>, ceil_div(b->P * 32, 128), 128, 0, (int)b->P, b->d_frame_off, b->d_obs_off,
               b->wmax, b->e_obs, b->e_dyn, initialize, sqrt(Sigma), b->init_res, b->lam, b->lam_next, b->active,
-              b->ntrials, b->flags, b->gate_arg, e_prior);
+              b->ntrials, b->flags, b->gate_arg, e_prior, nullptr, nullptr);
   }
   return VINSAT_OK;
 }

@@ -52,6 +52,8 @@ int launch_solve_retract(vinsat_batch* b, int initialize);
 int launch_solve_init_only(vinsat_batch* b);
 int launch_retract_only(vinsat_batch* b);
 int launch_accept(vinsat_batch* b, int initialize, double Sigma, const double* e_prior = nullptr);
+// stage 1 of the long-arc sums: part[chunk][3]; mode 0 linearisation / 1 trial; hi > lo: owned frames of a window batch
+int launch_sum_partials(vinsat_batch* b, int mode, int initialize, const double* e_prior, int64_t lo, int64_t hi);
 // ---- prior.cu (BA_reg) ----
 int launch_prior_linearize(vinsat_batch* b, double vc, double qc);   // srec += prior blocks; e_pr_init[f] = sum |r_prior|
 int launch_prior_trial(vinsat_batch* b, double vc, double qc);       // e_pr[f] = sum |r_prior(st_new)|

@@ -30,35 +30,28 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// partial sums over the OWNED frames (one warp, fixed order => deterministic)
+// sums over the OWNED frames: stage 1 = k_sum_partials (kernels_solve.cu: one CTA per chunk of kSumChunk frames -> part[c][3]),
+// stage 2 = this kernel, one CTA adding the chunk sums in a fixed order (deterministic).  A single warp walking the window took
+// 11 ms per call at 1.2 M frames per rank.
 //   which=0: sums[0] = sum grec[f][27] (|r_obs| unweighted), sums[1] = sum_{owned pairs} |r_pred| (7 components)
 //   which=1: sums[0] = sum e_obs[f],                         sums[1] = sum_{owned pairs} e_dyn[f]
 // The linearisation's sums go to sums[0..1], the trial's to sums[2..3] (the weighted observation sum already divided
 // by the GLOBAL largest weight, which the all-reduce(MAX) after ASSEMBLE left in wmax), so that ONE all-reduce of the
 // four doubles and ONE host read at the end of a trial carry everything the accept test needs.
-__global__ void __launch_bounds__(32) k_la_sums(int64_t lo, int64_t hi, int which, int initialize,
-                                                const int32_t* __restrict__ gap, const double* __restrict__ grec,
-                                                const double* __restrict__ drec, const double* __restrict__ e_obs,
-                                                const double* __restrict__ e_dyn,
-                                                const unsigned long long* __restrict__ wmax, double* __restrict__ sums) {
-  const int lane = threadIdx.x;
+__global__ void __launch_bounds__(256) k_la_sums_final(int n_chunks, int which, const double* __restrict__ part,
+                                                       const unsigned long long* __restrict__ wmax, double* __restrict__ sums) {
+  __shared__ double s_part[2][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double so = 0.0, sd = 0.0;
-  for (int64_t f = lo + lane; f < hi; f += 32) {
-    const bool pair = !initialize && gap[f] > 0;
-    if (which == 0) {
-      so += grec[f * VS_GREC + 27];
-      if (pair) {
-        const double* d = drec + f * VS_DREC + 36;
-        sd += fabs(d[0]) + fabs(d[1]) + fabs(d[2]) + fabs(d[3]) + fabs(d[4]) + fabs(d[5]) + fabs(d[6]);
-      }
-    } else {
-      so += e_obs[f];
-      if (pair) sd += e_dyn[f];
-    }
-  }
+  for (int c = tid; c < n_chunks; c += 256) { so += part[(int64_t)c * 3]; sd += part[(int64_t)c * 3 + 1]; }
   so = warp_sum_d(so);
   sd = warp_sum_d(sd);
-  if (lane == 0) {
+  if (lane == 0) { s_part[0][warp] = so; s_part[1][warp] = sd; }
+  __syncthreads();
+  if (tid == 0) {
+    so = 0.0; sd = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { so += s_part[0][w]; sd += s_part[1][w]; }
     if (which == 0) { sums[0] = so; sums[1] = sd; sums[2] = 0.0; sums[3] = 0.0; }
     else {
       const unsigned long long wb = wmax[0];
@@ -165,6 +158,27 @@ int vinsat_la_alloc_reduced(vinsat_batch* b, int64_t S_total, int64_t n_ranks) {
   VS_TRY(la_alloc(ctx, &b->la_chain, 4));
   const int32_t h[4] = {0, (int32_t)S_total, 0, 0};
   VS_CUDA(ctx, cudaMemcpy(b->la_chain, h, sizeof(h), cudaMemcpyHostToDevice));
+  // second partition level over the gathered reduced chain (every rank solves it redundantly): with thousands of segments per
+  // rank one warp walking S_total separators would dominate the trial
+  {
+    const Level2Host hp = plan_level2({0}, {(int32_t)S_total}, {0}, level2_min_separators());
+    Level2& L = b->la_l2;
+    L.n = (int64_t)hp.a.size();
+    L.n_chains = (int64_t)hp.red_a.size();
+    if (L.n > 0) {
+      VS_TRY(la_alloc(ctx, &L.a, L.n)); VS_TRY(la_alloc(ctx, &L.b, L.n)); VS_TRY(la_alloc(ctx, &L.left, L.n));
+      VS_TRY(la_alloc(ctx, &L.prob, L.n)); VS_TRY(la_alloc(ctx, &L.has_next, L.n));
+      VS_TRY(la_alloc(ctx, &L.red_a, L.n_chains)); VS_TRY(la_alloc(ctx, &L.red_b, L.n_chains)); VS_TRY(la_alloc(ctx, &L.red_prob, L.n_chains));
+      VS_TRY(la_alloc(ctx, &L.redrec, L.n * VS_RREC)); VS_TRY(la_alloc(ctx, &L.rsys, L.n * VS_SREC));
+      VS_TRY(la_alloc(ctx, &L.rlow, L.n * 81)); VS_TRY(la_alloc(ctx, &L.rwrec, L.n * VS_WREC));
+      auto up = [&](int32_t* dst, const std::vector<int32_t>& v) {
+        return cudaMemcpy(dst, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+      };
+      VS_CUDA(ctx, up(L.a, hp.a)); VS_CUDA(ctx, up(L.b, hp.b)); VS_CUDA(ctx, up(L.left, hp.left)); VS_CUDA(ctx, up(L.prob, hp.prob));
+      VS_CUDA(ctx, up(L.has_next, hp.has_next)); VS_CUDA(ctx, up(L.red_a, hp.red_a)); VS_CUDA(ctx, up(L.red_b, hp.red_b));
+      VS_CUDA(ctx, up(L.red_prob, hp.red_prob));
+    }
+  }
   return VINSAT_OK;
 }
 
@@ -205,8 +219,9 @@ int vinsat_la_stage(vinsat_batch* b, int stage, int64_t i0, int64_t i1, double d
       b->srec_valid = true; b->last_sigma = d0; b->last_initialize = (int)i0; b->have_iter = true;
       return launch_system_build(b, (int)i0, d0, vc);                             // i0 = initialize, d0 = Sigma
     case VINSAT_LA_SUMS_INIT:
-      VS_LAUNCH(ctx, F_ACCEPT, k_la_sums, 1, 32, 0, b->own_lo, b->own_hi, 0, (int)i0, b->gap, b->grec, b->drec, b->e_obs,
-                b->e_dyn, b->wmax, b->la_sums);
+      VS_TRY(launch_sum_partials(b, 0, (int)i0, nullptr, b->own_lo, b->own_hi));
+      VS_LAUNCH(ctx, F_ACCEPT, k_la_sums_final, 1, 256, 0, (int)ceil_div(b->own_hi - b->own_lo, kSumChunk), 0, b->sum_part, b->wmax,
+                b->la_sums);
       return VINSAT_OK;
     case VINSAT_LA_SET_LAM:
       VS_LAUNCH(ctx, F_ACCEPT, k_la_set_lam, 1, 1, 0, d0, b->lam, b->active);
@@ -242,8 +257,9 @@ int vinsat_la_stage(vinsat_batch* b, int stage, int64_t i0, int64_t i1, double d
       return VINSAT_OK;
     case VINSAT_LA_SUMS_TRIAL:
       if (i1) VS_CUDA(ctx, cudaMemsetAsync(b->la_sums, 0, 2 * sizeof(double), ctx->stream));   // i1: drop the (already reduced) init sums
-      VS_LAUNCH(ctx, F_ACCEPT, k_la_sums, 1, 32, 0, b->own_lo, b->own_hi, 1, (int)i0, b->gap, b->grec, b->drec, b->e_obs,
-                b->e_dyn, b->wmax, b->la_sums);
+      VS_TRY(launch_sum_partials(b, 1, (int)i0, nullptr, b->own_lo, b->own_hi));
+      VS_LAUNCH(ctx, F_ACCEPT, k_la_sums_final, 1, 256, 0, (int)ceil_div(b->own_hi - b->own_lo, kSumChunk), 1, b->sum_part, b->wmax,
+                b->la_sums);
       return VINSAT_OK;
     case VINSAT_LA_COMMIT:
       std::swap(b->st, b->st_new);

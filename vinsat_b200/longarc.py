@@ -36,11 +36,19 @@ def plan_windows(T, world):
     return [(T * r // world, T * (r + 1) // world) for r in range(world)]
 
 
-def plan_segments(T, world):
-    """Common number of segments per rank: segment length ~ sqrt(0.67 T) balances the parallel interior sweeps
-    (len x ~3 us) against the sequential reduced chain (world x segments x ~2 us)."""
+def plan_segments(T, world, sm_count=148):
+    """Common number of segments per rank.  Short arcs: segment length ~ sqrt(0.67 T) balances the parallel interior
+    sweeps (len x ~3 us) against the sequential reduced chain (world x segments x ~2 us).  Long arcs: as many segments as a GPU
+    runs chains at once (8 one-warp CTAs x 3 chains per SM), each at least 24 frames long -- the gathered reduced chain is then
+    partitioned a second time inside the library (`Level2`, csrc/batch.h) instead of being walked by one warp."""
+    import os
     seg_len = max(8.0, math.sqrt(0.67 * T))
-    return max(1, int(round((T / world) / seg_len)))
+    S = max(1, int(round((T / world) / seg_len)))
+    l2_min = int(os.environ.get("VINSAT_L2_MIN", "256"))
+    S2 = min(8 * sm_count * 3, (T // world) // 24)
+    if l2_min > 0 and S2 * world >= l2_min and S2 > S:
+        S = S2
+    return S
 
 
 def window_arrays(pr, lo, hi):

@@ -49,8 +49,11 @@ def _project_truth(states, xyz, intr, ii):
 
 
 def make_batch(P, T, K, seed0=0, gap_max=20, sigma_px=1.0, lm_sigma_km=60.0, pos_sigma=100.0,
-               rot_sigma=0.2, vel_frac=0.1, conf_lo=1.0, faithful_cum_rot=False, empty_frame_frac=0.0):
+               rot_sigma=0.2, vel_frac=0.1, conf_lo=1.0, faithful_cum_rot=False, empty_frame_frac=0.0, orbit_fn=None):
     """P independent problems with T frames and K observations per frame each.
+
+    `orbit_fn(x0 (P,6), n_steps) -> (P, n_steps+1, 6)`, when given, replaces the host RK4 loop that integrates the truth
+    orbits at 1 Hz (e.g. `Context.orbit_propagate` for arcs of millions of frames, where the Python loop takes minutes).
 
     Returns a list of P dicts with keys: states0 (T,10) perturbed guess, states_gt (T,10),
     velocities (T,3) [gt, forward difference as process_ground_truths], cum_rot (T,4),
@@ -65,6 +68,11 @@ def make_batch(P, T, K, seed0=0, gap_max=20, sigma_px=1.0, lm_sigma_km=60.0, pos
     ptr = np.zeros(P, dtype=np.int64)
     ar = np.arange(P)
     full = [] if faithful_cum_rot else None
+    if orbit_fn is not None and full is None:
+        traj = np.asarray(orbit_fn(x, D))                        # (P, D+1, 6): states at t = 0 .. D
+        for p in range(P):
+            pos_t[p], vel_true[p], pos_t1[p] = traj[p, time_idx[p], 0:3], traj[p, time_idx[p], 3:6], traj[p, time_idx[p] + 1, 0:3]
+        D = 0
     for t in range(D):
         if full is not None:
             full.append(x[:, 0:3].copy())
