@@ -153,3 +153,18 @@ def test_window_schedule_reproduces_reference_times(name):
     if t_final[-1] < len(time_idx2):
         lens.append(len(time_idx2) - t_final[-1])
     assert np.array_equal(np.array(lens), g["sv_times_len"])
+
+
+def test_long_arc_segment_plan(monkeypatch):
+    """vinsat_b200.longarc.plan_segments: short arcs keep ~sqrt(0.67 T)-frame segments (one sequential reduced chain); long arcs
+    get one wave of chains per GPU (8 x 3 per SM), at least 24 frames each, once the gathered reduced chain is long enough for
+    the library's second partition level (VINSAT_L2_MIN, default 256 separators)."""
+    from vinsat_b200 import longarc
+    monkeypatch.delenv("VINSAT_L2_MIN", raising=False)
+    assert longarc.plan_segments(120, 2) == 7                      # 60 frames per rank / sqrt(80.4)
+    assert longarc.plan_segments(3000, 1) == 67                    # 3000 // 24 = 125 < 256: one level
+    assert longarc.plan_segments(100_000, 2) == 50_000 // 24       # 2083 per rank, 4166 separators: two levels
+    assert longarc.plan_segments(2_400_000, 2) == 8 * 148 * 3      # capped at one wave of chains
+    monkeypatch.setenv("VINSAT_L2_MIN", "0")
+    assert longarc.plan_segments(100_000, 2) == round(50_000 / (0.67 * 100_000) ** 0.5)
+    assert longarc.plan_windows(2_400_000, 8)[-1] == (2_100_000, 2_400_000)
