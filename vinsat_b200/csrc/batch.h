@@ -43,7 +43,7 @@ inline Level2Host plan_level2(const std::vector<int32_t>& red_a, const std::vect
   if (!any) return h;
   for (size_t p = 0; p < red_a.size(); p++) {
     const int64_t S = red_b[p] - red_a[p];
-    const int64_t S2 = S >= min_sep ? std::max<int64_t>(2, llround(sqrt((double)S))) : (S > 0 ? 1 : 0);
+    const int64_t S2 = S >= min_sep ? std::min<int64_t>(S, std::max<int64_t>(2, llround(sqrt((double)S)))) : (S > 0 ? 1 : 0);
     h.red_a.push_back((int32_t)h.a.size());
     for (int64_t k = 0; k < S2; k++) {
       const int64_t lo = red_a[p] + (S * k) / S2, hi = red_a[p] + (S * (k + 1)) / S2;   // elements [lo, hi), separator hi-1
