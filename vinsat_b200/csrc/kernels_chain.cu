@@ -923,6 +923,226 @@ __global__ void __launch_bounds__(128) k_seg_backsub(int n_chains, const int32_t
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Bulk-copy rings.  The two backward passes of the partitioned solve stream one contiguous 1376-byte W|y|Z record per
+// step through a per-warp shared-memory ring.  Fed with 8-byte cp.async that is 171 LDGSTS per record = 6 per lane per
+// step at 8 LSU cycles each -- with 24-32 warps per SM the load/store unit, not the arithmetic, set the step time
+// (~2000 cycles).  Here ONE lane issues ONE cp.async.bulk per record (the copy engine moves it, completion is counted
+// in bytes on the slot's mbarrier) and every lane waits on the barrier's phase.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+constexpr int kBulkRing = 4;
+constexpr uint32_t kWrecBytes = VS_WREC * sizeof(double);      // 1376: a multiple of 16, records are 16-byte aligned
+static_assert(kWrecBytes % 16 == 0, "cp.async.bulk moves multiples of 16 bytes");
+
+// out[r] = sum_k M[k*9 + r] * v[k] for a 9x9 block stored with stride 9 (as it lies in a wrec record).  Rows start
+// 16-byte aligned for even k and 8 bytes past that for odd k; the 16-byte loads are placed accordingly.
+__device__ __forceinline__ void matvec9_s9(const double* __restrict__ M, const double* v, double* out) {
+#pragma unroll
+  for (int r = 0; r < 9; r++) out[r] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const double vk = v[k];
+    const double* row = M + k * 9;
+    if ((k & 1) == 0) {
+#pragma unroll
+      for (int r2 = 0; r2 < 4; r2++) {
+        const double2 m = *reinterpret_cast<const double2*>(row + 2 * r2);
+        out[2 * r2] = fma(m.x, vk, out[2 * r2]);
+        out[2 * r2 + 1] = fma(m.y, vk, out[2 * r2 + 1]);
+      }
+      out[8] = fma(row[8], vk, out[8]);
+    } else {
+      out[0] = fma(row[0], vk, out[0]);
+#pragma unroll
+      for (int r2 = 0; r2 < 4; r2++) {
+        const double2 m = *reinterpret_cast<const double2*>(row + 1 + 2 * r2);
+        out[1 + 2 * r2] = fma(m.x, vk, out[1 + 2 * r2]);
+        out[2 + 2 * r2] = fma(m.y, vk, out[2 + 2 * r2]);
+      }
+    }
+  }
+}
+
+// k_seg_backrec with the bulk ring (same arithmetic, same order).
+__global__ void __launch_bounds__(128) k_seg_backrec_bulk(ChainArgs A) {
+  __shared__ __align__(128) double s_ring[4][kBulkRing][VS_WREC];
+  __shared__ __align__(16) double s_M[4][9 * kMS];
+  __shared__ __align__(8) unsigned long long s_bar[4][kBulkRing];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * 4 + warp;
+  if (ch >= A.n_chains) return;
+  if (A.active && !A.active[A.ch_prob[ch]]) return;
+  const int a = A.ch_a[ch], e = A.ch_b[ch], left = A.ch_left[ch];
+  double* rq = A.redrec + (int64_t)ch * VS_RREC + 171;
+  if (left < 0) {
+    for (int idx = lane; idx < 171; idx += 32) rq[idx] = 0.0;
+    return;
+  }
+  const double* Ul = A.rec + (int64_t)left * VS_SREC + 81;
+  if (e <= a) {      // no interior: Ur = U_left, Dr = br = 0
+    for (int idx = lane; idx < 171; idx += 32) rq[idx] = (idx >= 81 && idx < 162) ? Ul[idx - 81] : 0.0;
+    return;
+  }
+  double (*ring)[VS_WREC] = s_ring[warp];
+  const uint32_t bar0 = smem_u32(&s_bar[warp][0]), ring0 = smem_u32(&ring[0][0]);
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < kBulkRing; d++) mbar_init(bar0 + 8 * d, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  auto issue = [&](int i, int slot) {          // wrec of interior element i -> ring[slot], one bulk copy
+    if (lane == 0 && i >= a) {
+      mbar_expect_tx(bar0 + 8 * slot, kWrecBytes);
+      bulk_g2s(ring0 + slot * kWrecBytes, A.wrec + (int64_t)i * VS_WREC, kWrecBytes, bar0 + 8 * slot);
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < kBulkRing; d++) issue(e - 2 - d, d);
+  double* M = s_M[warp];
+  const bool isW = lane < 9, isY = lane == 9, isZ = lane >= 10 && lane < 19;
+  const int cc = isW ? lane : (isZ ? lane - 10 : 0);
+  const int off = isW ? cc * 9 : (isY ? 81 : 90 + cc * 9);      // own column inside a wrec record: W col cc | y | Z col cc
+  const bool act = lane < 19;
+  double h[9], own[9];
+  {
+    const double* w = A.wrec + (int64_t)(e - 1) * VS_WREC;
+#pragma unroll
+    for (int r = 0; r < 9; r++) h[r] = act ? w[off + r] : 0.0;
+  }
+  uint32_t phases = 0;
+  int slot = 0;
+  for (int i = e - 2; i >= a; i--) {
+    mbar_wait(bar0 + 8 * slot, (phases >> slot) & 1u);
+    phases ^= 1u << slot;
+    const double* R = ring[slot];              // R[c*9 + r] = W_i[r][c]
+#pragma unroll
+    for (int r = 0; r < 9; r++) own[r] = (act && !isW) ? R[off + r] : 0.0;
+    double o[9];
+    matvec9_s9(R, h, o);
+#pragma unroll
+    for (int r = 0; r < 9; r++) h[r] = own[r] - o[r];
+    __syncwarp();                              // every lane has read the slot before it is refilled
+    issue(i - kBulkRing, slot);
+    slot = (slot + 1 == kBulkRing) ? 0 : slot + 1;
+  }
+  // M[k*kMS + r] = U_left[r][k]
+  for (int idx = lane; idx < 81; idx += 32) { const int r = idx / 9, k = idx % 9; M[k * kMS + r] = Ul[idx]; }
+  __syncwarp();
+  double o[9];
+  matvec9(M, h, o);
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    if (isZ) rq[r * 9 + cc] = -o[r];            // Dr
+    else if (isW) rq[81 + r * 9 + cc] = -o[r];  // Ur
+    else if (isY) rq[162 + r] = -o[r];          // br
+  }
+}
+
+// k_seg_backsub with the bulk ring (same arithmetic, same order).
+__global__ void __launch_bounds__(128) k_seg_backsub_bulk(int n_chains, const int32_t* __restrict__ ch_a,
+                                                          const int32_t* __restrict__ ch_b,
+                                                          const int32_t* __restrict__ ch_left,
+                                                          const int32_t* __restrict__ ch_prob,
+                                                          const int32_t* __restrict__ active,
+                                                          const double* __restrict__ wrec, double* __restrict__ delta) {
+  __shared__ __align__(128) double s_ring[4][kBulkRing][VS_WREC];
+  __shared__ __align__(8) unsigned long long s_bar[4][kBulkRing];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ch = blockIdx.x * 4 + warp;
+  if (ch >= n_chains) return;
+  if (active && !active[ch_prob[ch]]) return;
+  const int a = ch_a[ch], b = ch_b[ch], left = ch_left[ch];
+  if (b <= a) return;
+  double (*ring)[VS_WREC] = s_ring[warp];
+  const uint32_t bar0 = smem_u32(&s_bar[warp][0]), ring0 = smem_u32(&ring[0][0]);
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < kBulkRing; d++) mbar_init(bar0 + 8 * d, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  auto issue = [&](int i, int slot) {
+    if (lane == 0 && i >= a) {
+      mbar_expect_tx(bar0 + 8 * slot, kWrecBytes);
+      bulk_g2s(ring0 + slot * kWrecBytes, wrec + (int64_t)i * VS_WREC, kWrecBytes, bar0 + 8 * slot);
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < kBulkRing; d++) issue(b - 1 - d, d);
+  double x[9], xl[9];
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    x[r] = delta[(int64_t)b * 9 + r];
+    xl[r] = left >= 0 ? delta[(int64_t)left * 9 + r] : 0.0;
+  }
+  uint32_t phases = 0;
+  int slot = 0;
+  for (int i = b - 1; i >= a; i--) {
+    mbar_wait(bar0 + 8 * slot, (phases >> slot) & 1u);
+    phases ^= 1u << slot;
+    double dr = 0.0;
+    if (lane < 9) {
+      const double* w = ring[slot];
+      double zr = 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) zr = fma(w[90 + k * 9 + lane], xl[k], zr);     // off the critical path
+      dr = w[81 + lane] - zr;
+#pragma unroll
+      for (int k = 0; k < 9; k++) dr = fma(-w[k * 9 + lane], x[k], dr);
+    }
+    __syncwarp();                              // the slot has been read before it is refilled
+    issue(i - kBulkRing, slot);
+#pragma unroll
+    for (int k = 0; k < 9; k++) x[k] = __shfl_sync(0xffffffffu, dr, k);
+    if (lane < 9) delta[(int64_t)i * 9 + lane] = dr;
+    slot = (slot + 1 == kBulkRing) ? 0 : slot + 1;
+  }
+}
+
+// VINSAT_NO_BULK_RING=1 selects the cp.async (LDGSTS) rings instead.
+static bool use_bulk_ring() {
+  static const bool on = getenv("VINSAT_NO_BULK_RING") == nullptr;
+  return on;
+}
+
+static int launch_backrec(vinsat_ctx* ctx, const ChainArgs& A) {
+  if (use_bulk_ring()) VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec_bulk, ceil_div(A.n_chains, 4), 128, 0, A);
+  else VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
+  return VINSAT_OK;
+}
+
+static int launch_backsub(vinsat_ctx* ctx, int64_t n, const int32_t* a, const int32_t* b, const int32_t* left,
+                          const int32_t* prob, const int32_t* active, const double* wrec, double* delta) {
+  if (use_bulk_ring()) VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub_bulk, ceil_div(n, 4), 128, 0, (int)n, a, b, left, prob, active, wrec, delta);
+  else VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div(n, 4), 128, 0, (int)n, a, b, left, prob, active, wrec, delta);
+  return VINSAT_OK;
+}
+
 // reduced system of a frame-window sharded arc from the all-gathered per-segment packs
 //   pack[s] = { redrec (VS_RREC) | system record of the separator frame (VS_SREC) }, one problem, global order
 __global__ void __launch_bounds__(256) k_reduced_build_packed(int n_seg, const double* __restrict__ pack,
@@ -971,15 +1191,14 @@ int launch_seg_forward(vinsat_batch* b) {
   if (b->n_seg == 0) return VINSAT_OK;
   ChainArgs A = seg_args(b);
   VS_TRY(launch_forward<true>(ctx, A));
-  VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
+  VS_TRY(launch_backrec(ctx, A));
   return VINSAT_OK;
 }
 
 int launch_seg_backsub(vinsat_batch* b) {
   vinsat_ctx* ctx = b->ctx;
   if (b->n_seg == 0) return VINSAT_OK;
-  VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div((int64_t)b->n_seg, 4), 128, 0, (int)b->n_seg, b->seg_a, b->seg_b,
-            b->seg_left, b->seg_prob, b->active, b->wrec, b->delta);
+  VS_TRY(launch_backsub(ctx, b->n_seg, b->seg_a, b->seg_b, b->seg_left, b->seg_prob, b->active, b->wrec, b->delta));
   return VINSAT_OK;
 }
 
@@ -1012,7 +1231,7 @@ int launch_level2_solve(vinsat_ctx* ctx, const Level2& L, const int32_t* active,
   A.out_index = nullptr;
   A.lam32_last = nullptr;
   VS_TRY(launch_forward<true>(ctx, A));
-  VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
+  VS_TRY(launch_backrec(ctx, A));
   VS_LAUNCH(ctx, F_SOLVE, k_reduced_build, ceil_div(L.n * 192, 256), 256, 0, (int)L.n, L.b, L.left, L.prob, L.has_next, active,
             (const double*)nullptr, rsys, L.redrec, L.rsys, L.rlow);
   ChainArgs R;
@@ -1029,7 +1248,7 @@ int launch_level2_solve(vinsat_ctx* ctx, const Level2& L, const int32_t* active,
   R.lam32_last = nullptr;
   VS_TRY(launch_forward<false>(ctx, R));
   VS_LAUNCH(ctx, F_SOLVE, k_chain_backward, ceil_div(R.n_chains, 4), 128, 0, R);
-  VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div(L.n, 4), 128, 0, (int)L.n, L.a, L.b, L.left, L.prob, active, rwrec, xsep);
+  VS_TRY(launch_backsub(ctx, L.n, L.a, L.b, L.left, L.prob, active, rwrec, xsep));
   return VINSAT_OK;
 }
 
@@ -1094,15 +1313,14 @@ int launch_chain_solve(vinsat_batch* b) {
   A.n_chains = (int)b->n_seg;
   A.ch_a = b->seg_a; A.ch_b = b->seg_b; A.ch_left = b->seg_left; A.ch_prob = b->seg_prob;
   VS_TRY(launch_forward<true>(ctx, A));
-  VS_LAUNCH(ctx, F_SOLVE, k_seg_backrec, ceil_div(A.n_chains, 4), 128, 0, A);
+  VS_TRY(launch_backrec(ctx, A));
   VS_LAUNCH(ctx, F_SOLVE, k_reduced_build, ceil_div((int64_t)b->n_seg * 192, 256), 256, 0, (int)b->n_seg, b->seg_b,
             b->seg_left, b->seg_prob, b->seg_has_next, b->active, b->lam, b->srec, b->redrec, b->rsys, b->rlow);
   if (b->l2.n > 0) {
     VS_TRY(launch_level2_solve(ctx, b->l2, b->active, b->rsys, b->rlow, b->rwrec, b->xsep));
     VS_LAUNCH(ctx, F_SOLVE, k_sep_scatter, ceil_div(b->n_seg * 9, 128), 128, 0, (int)b->n_seg, b->seg_b, b->seg_prob, b->active,
               b->xsep, b->delta);
-    VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div((int64_t)b->n_seg, 4), 128, 0, (int)b->n_seg, b->seg_a, b->seg_b,
-              b->seg_left, b->seg_prob, b->active, b->wrec, b->delta);
+    VS_TRY(launch_backsub(ctx, b->n_seg, b->seg_a, b->seg_b, b->seg_left, b->seg_prob, b->active, b->wrec, b->delta));
     return VINSAT_OK;
   }
   ChainArgs R;
@@ -1119,8 +1337,7 @@ int launch_chain_solve(vinsat_batch* b) {
   R.lam32_last = nullptr;
   VS_TRY(launch_forward<false>(ctx, R));
   VS_LAUNCH(ctx, F_SOLVE, k_chain_backward, ceil_div(R.n_chains, 4), 128, 0, R);
-  VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div((int64_t)b->n_seg, 4), 128, 0, (int)b->n_seg, b->seg_a, b->seg_b,
-            b->seg_left, b->seg_prob, b->active, b->wrec, b->delta);
+  VS_TRY(launch_backsub(ctx, b->n_seg, b->seg_a, b->seg_b, b->seg_left, b->seg_prob, b->active, b->wrec, b->delta));
   return VINSAT_OK;
 }
 
