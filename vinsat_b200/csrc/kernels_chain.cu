@@ -1138,8 +1138,14 @@ static int launch_backrec(vinsat_ctx* ctx, const ChainArgs& A) {
 
 static int launch_backsub(vinsat_ctx* ctx, int64_t n, const int32_t* a, const int32_t* b, const int32_t* left,
                           const int32_t* prob, const int32_t* active, const double* wrec, double* delta) {
-  if (use_bulk_ring()) VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub_bulk, ceil_div(n, 4), 128, 0, (int)n, a, b, left, prob, active, wrec, delta);
-  else VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div(n, 4), 128, 0, (int)n, a, b, left, prob, active, wrec, delta);
+  // measured on a 2.4 M-frame arc (profiles/r02_longarc_2400k_kernels_bulk.json vs ..._level2.json): with 3552 chains in flight
+  // the bulk ring is SLOWER here (0.90 vs 0.76 ms: a step is short, four bulk copies ahead do not cover the copy engine's
+  // latency) while the backward recurrence gains (0.92 vs 1.28 ms); with 60 chains (second level, latency bound) it is
+  // faster (21 vs 32 us).  Hence: bulk ring for fewer than 1024 chains, LDGSTS ring above.
+  if (use_bulk_ring() && n < 1024)
+    VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub_bulk, ceil_div(n, 4), 128, 0, (int)n, a, b, left, prob, active, wrec, delta);
+  else
+    VS_LAUNCH(ctx, F_SOLVE, k_seg_backsub, ceil_div(n, 4), 128, 0, (int)n, a, b, left, prob, active, wrec, delta);
   return VINSAT_OK;
 }
 
